@@ -1,0 +1,142 @@
+"""ctypes binding of libnerfb200.so (the C ABI declared in include/nerfb200.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``make -C csrc``.  There is no CPU
+fallback: if the shared object is missing, loading raises, and every wrapper raises
+``RuntimeError`` with the library's error text on a non-zero status.
+"""
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnerfb200.so")
+CSRC_DIR = os.path.join(_HERE, "csrc")
+
+# ---- mirrors of csrc/mlp.h -----------------------------------------------------------------
+NB_MAX_OPS = 40
+NB_MAX_CHUNKS = 6
+NB_MAX_BLOCKS = 3
+NB_TILE_ROWS = 128
+NB_SLAB_BYTES = 128 * 128
+NB_N_SLABS = 6
+NB_RING_STAGE_BYTES = 272 * 128
+
+EPI_RELU, EPI_LINEAR, EPI_LINEAR_SIGMA, EPI_RGB, EPI_RGB_SIGMA, EPI_RELU_SIGMA = range(6)
+BEPI_MASK, BEPI_PLAIN, BEPI_PLAIN_SIGMA, BEPI_MASK_SIGMA, BEPI_NONE = range(5)
+PE_IDENTITY, PE_FOURIER, PE_INTEGRATED = range(3)
+COMPOSITE_BARF, COMPOSITE_NERFACC = 0, 1
+
+
+class NbBlock(C.Structure):
+    _fields_ = [("tmem_col", C.c_int16), ("n", C.c_int16), ("row0", C.c_int16), ("accum_in", C.c_int16)]
+
+
+class NbOp(C.Structure):
+    _fields_ = [
+        ("n_chunks", C.c_int8), ("n_blocks", C.c_int8), ("epi", C.c_int8), ("out_chunks", C.c_int8),
+        ("a_src", C.c_int8 * NB_MAX_CHUNKS), ("k16", C.c_int8 * NB_MAX_CHUNKS),
+        ("w_rows", C.c_int16 * NB_MAX_CHUNKS), ("w_off", C.c_int32 * NB_MAX_CHUNKS),
+        ("blocks", NbBlock * NB_MAX_BLOCKS),
+        ("bias_off", C.c_int32), ("stash_slab", C.c_int32), ("mask_word", C.c_int32),
+        ("out_width", C.c_int32),
+    ]
+
+
+class NbProgram(C.Structure):
+    _fields_ = [("n_ops", C.c_int32), ("stash_slabs_per_tile", C.c_int32),
+                ("mask_words_per_tile", C.c_int32), ("reserved", C.c_int32),
+                ("ops", NbOp * NB_MAX_OPS)]
+
+
+class NbPeCfg(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("levels", C.c_int32), ("include_identity", C.c_int32),
+                ("use_mask", C.c_int32), ("distribute_variance", C.c_int32), ("scale", C.c_float),
+                ("pixel_width_sigma", C.c_float), ("slab", C.c_int32), ("stash_slab", C.c_int32)]
+
+
+class NbMlpInputs(C.Structure):
+    _fields_ = [("N", C.c_int64), ("S", C.c_int32), ("t_mode", C.c_int32),
+                ("ray_o", C.c_void_p), ("ray_d", C.c_void_p), ("t_start", C.c_void_p),
+                ("t_end", C.c_void_p), ("pixel_width", C.c_void_p), ("pos", C.c_void_p),
+                ("dir", C.c_void_p), ("pixel_width_per_sample", C.c_int32), ("reserved", C.c_int32)]
+
+
+class NbPackChunk(C.Structure):
+    _fields_ = [("base", C.c_int64), ("row_stride", C.c_int32), ("col_stride", C.c_int32),
+                ("n_rows", C.c_int32), ("n_cols", C.c_int32), ("rows_padded", C.c_int32),
+                ("dst_off", C.c_int32)]
+
+
+class NbPackBias(C.Structure):
+    _fields_ = [("base", C.c_int64), ("n", C.c_int32), ("n_padded", C.c_int32),
+                ("dst_off", C.c_int32), ("reserved", C.c_int32)]
+
+
+_lib = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compiles csrc/*.cu for sm_100a into libnerfb200.so (nvcc cross-compiles without a GPU)."""
+    res = subprocess.run(["make", "-C", CSRC_DIR, "-j8"], capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout[-4000:])
+        print(res.stderr[-4000:])
+    if res.returncode != 0:
+        raise RuntimeError("building libnerfb200.so failed")
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.nerfb200_last_error.restype = C.c_char_p
+        _lib.nerfb200_launch_count.restype = C.c_longlong
+        _declare(_lib)
+    return _lib
+
+
+def _declare(L):
+    vp, i32, f64, f32 = C.c_void_p, C.c_int, C.c_double, C.c_float
+    L.nerfb200_sample_uniform.argtypes = [f64, f64, i32, i32, vp, vp, f64, vp, vp, vp]
+    L.nerfb200_composite_fwd.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]
+    L.nerfb200_composite_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp]
+    L.nerfb200_resample_alloc.argtypes = [vp, vp, vp, i32, i32, i32, f64, vp, vp, vp, vp, vp]
+    L.nerfb200_resample_fallback.argtypes = [vp, f64, f64, i32, i32, vp, vp, vp, vp]
+    L.nerfb200_resample_icdf.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp]
+    L.nerfb200_pose_fwd.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp]
+    L.nerfb200_pose_bwd.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp, vp, vp]
+    L.nerfb200_so3_to_SO3.argtypes = [vp, i32, vp, vp]
+    L.nerfb200_mlp_pack.argtypes = [vp, vp, i32, vp, vp, i32, vp, vp]
+    L.nerfb200_mlp_fwd.argtypes = [vp, vp, vp, C.POINTER(NbMlpInputs), C.POINTER(NbPeCfg),
+                                   C.POINTER(NbPeCfg), vp, vp, f32, vp, vp, vp, vp, vp]
+    L.nerfb200_pe_fwd.argtypes = [C.POINTER(NbPeCfg), vp, vp, vp, vp, vp, vp, C.c_longlong, vp, vp]
+    L.nerfb200_pe_bwd.argtypes = [C.POINTER(NbPeCfg), vp, vp, vp, vp, vp, vp, vp, C.c_longlong, vp, vp, vp]
+    for name in EXPORTS:
+        fn = getattr(L, name)
+        if name not in ("nerfb200_last_error", "nerfb200_launch_count"):
+            fn.restype = C.c_int
+
+
+# every symbol include/nerfb200.h declares (tests check that the library exports them all)
+EXPORTS = [
+    "nerfb200_last_error", "nerfb200_abi_version", "nerfb200_launch_count",
+    "nerfb200_sample_uniform", "nerfb200_composite_fwd", "nerfb200_composite_bwd",
+    "nerfb200_resample_alloc", "nerfb200_resample_fallback", "nerfb200_resample_icdf",
+    "nerfb200_pose_fwd", "nerfb200_pose_bwd", "nerfb200_so3_to_SO3",
+    "nerfb200_mlp_pack", "nerfb200_mlp_fwd", "nerfb200_pe_fwd", "nerfb200_pe_bwd",
+]
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = lib().nerfb200_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (status {status}): {msg}")
+
+
+def launch_count() -> int:
+    return int(lib().nerfb200_launch_count())

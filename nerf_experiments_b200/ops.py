@@ -1,0 +1,224 @@
+"""Thin torch wrappers over the C ABI (include/nerfb200.h): argument checking, raw pointers and
+the current CUDA stream in; tensors out.  The autograd Functions give the ops the gradients the
+reference obtains from PyTorch autograd.  CUDA only — there is no CPU path."""
+from typing import Optional
+
+import torch as th
+
+from . import _lib
+from ._lib import check, lib
+
+
+def _ptr(t: Optional[th.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return th.cuda.current_stream().cuda_stream
+
+
+def _f32(t: th.Tensor, name: str, shape=None) -> th.Tensor:
+    if not isinstance(t, th.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (nerfb200 has no CPU fallback)")
+    if t.dtype != th.float32:
+        raise RuntimeError(f"{name}: expected float32, got {t.dtype}")
+    t = t.contiguous()
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise RuntimeError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
+    return t
+
+
+def _i32(t: th.Tensor, name: str) -> th.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor")
+    return t.to(th.int32).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
+# a1 uniform sampling
+# ---------------------------------------------------------------------------------------------
+def sample_uniform(near: float, far: float, batch: int, n_samples: int, device,
+                   jitter: Optional[th.Tensor] = None, offset_u: Optional[th.Tensor] = None,
+                   offset_size: float = 0.0):
+    """t_start, t_end (B,S) — barf/model_interpolation.py:135-180 with explicit uniforms."""
+    t_start = th.empty((batch, n_samples), device=device, dtype=th.float32)
+    t_end = th.empty_like(t_start)
+    if jitter is not None:
+        jitter = _f32(jitter, "jitter", (batch, n_samples))
+    if offset_u is not None:
+        offset_u = _f32(offset_u.reshape(-1), "offset_u", (batch,))
+    with th.cuda.device(t_start.device):
+        check(lib().nerfb200_sample_uniform(float(near), float(far), batch, n_samples, _ptr(jitter),
+                                            _ptr(offset_u), float(offset_size), _ptr(t_start),
+                                            _ptr(t_end), _stream()), "sample_uniform")
+    return t_start, t_end
+
+
+# ---------------------------------------------------------------------------------------------
+# a10 compositing
+# ---------------------------------------------------------------------------------------------
+def composite_fwd(sigma, delta, rgb, t_mid=None, flavour=_lib.COMPOSITE_BARF, want_w=True,
+                  want_opacity=False, want_depth=False):
+    B, S = sigma.shape
+    sigma = _f32(sigma, "sigma", (B, S))
+    delta = _f32(delta, "delta", (B, S))
+    rgb = _f32(rgb, "rgb", (B, S, 3))
+    if t_mid is not None:
+        t_mid = _f32(t_mid, "t_mid", (B, S))
+    out_rgb = th.empty((B, 3), device=sigma.device, dtype=th.float32)
+    out_w = th.empty((B, S), device=sigma.device, dtype=th.float32) if want_w else None
+    out_o = th.empty((B,), device=sigma.device, dtype=th.float32) if want_opacity else None
+    out_d = th.empty((B,), device=sigma.device, dtype=th.float32) if want_depth else None
+    with th.cuda.device(sigma.device):
+        check(lib().nerfb200_composite_fwd(_ptr(sigma), _ptr(delta), _ptr(rgb), _ptr(t_mid), B, S,
+                                           flavour, _ptr(out_rgb), _ptr(out_w), _ptr(out_o),
+                                           _ptr(out_d), _stream()), "composite_fwd")
+    return out_rgb, out_w, out_o, out_d
+
+
+def composite_bwd(sigma, delta, rgb, g_rgb, g_w=None, t_mid=None, g_opacity=None, g_depth=None,
+                  flavour=_lib.COMPOSITE_BARF):
+    B, S = sigma.shape
+    sigma = _f32(sigma, "sigma", (B, S))
+    delta = _f32(delta, "delta", (B, S))
+    rgb = _f32(rgb, "rgb", (B, S, 3))
+    g_rgb = _f32(g_rgb, "g_rgb", (B, 3))
+    g_w = None if g_w is None else _f32(g_w, "g_w", (B, S))
+    t_mid = None if t_mid is None else _f32(t_mid, "t_mid", (B, S))
+    g_opacity = None if g_opacity is None else _f32(g_opacity.reshape(-1), "g_opacity", (B,))
+    g_depth = None if g_depth is None else _f32(g_depth.reshape(-1), "g_depth", (B,))
+    d_sigma = th.empty((B, S), device=sigma.device, dtype=th.float32)
+    d_rgb = th.empty((B, S, 3), device=sigma.device, dtype=th.float32)
+    with th.cuda.device(sigma.device):
+        check(lib().nerfb200_composite_bwd(_ptr(sigma), _ptr(delta), _ptr(rgb), _ptr(t_mid),
+                                           _ptr(g_rgb), _ptr(g_w), _ptr(g_opacity), _ptr(g_depth),
+                                           B, S, flavour, _ptr(d_sigma), _ptr(d_rgb), _stream()),
+              "composite_bwd")
+    return d_sigma, d_rgb
+
+
+class _Composite(th.autograd.Function):
+    """rgb, weights = render(sigma, rgb_samples, delta) — barf/model_interpolation.py:316-353."""
+
+    @staticmethod
+    def forward(ctx, sigma, rgb, delta):
+        out_rgb, out_w, _, _ = composite_fwd(sigma, delta, rgb)
+        ctx.save_for_backward(sigma.detach(), rgb.detach(), delta.detach())
+        return out_rgb, out_w
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_w):
+        sigma, rgb, delta = ctx.saved_tensors
+        g_rgb = th.zeros_like(rgb[:, 0, :]) if g_rgb is None else g_rgb
+        d_sigma, d_rgb = composite_bwd(sigma, delta, rgb, g_rgb.contiguous(),
+                                       None if g_w is None else g_w.contiguous())
+        return d_sigma, d_rgb, None
+
+
+def render_rays(densities, colors, distances):
+    """Drop-in for NerfInterpolation._render_rays."""
+    return _Composite.apply(densities, colors, distances)
+
+
+# ---------------------------------------------------------------------------------------------
+# a11 deterministic resampling
+# ---------------------------------------------------------------------------------------------
+def resample_alloc(t_coarse, weights, delta_coarse, n_samples: int, near: float, far: float,
+                   fallback_u: Optional[th.Tensor] = None, want_counts: bool = False):
+    """t_start, t_end (B,Sf) [, counts (B,Sc) int32, fail_flag int32[1]] —
+    barf/model_interpolation.py:193-277, including its whole-batch equidistant fallback,
+    applied on the device without a host sync."""
+    B, Sc = t_coarse.shape
+    t_coarse = _f32(t_coarse.detach(), "t_coarse", (B, Sc))
+    weights = _f32(weights.detach(), "weights", (B, Sc))
+    delta_coarse = _f32(delta_coarse.detach(), "delta_coarse", (B, Sc))
+    dev = t_coarse.device
+    t_start = th.empty((B, n_samples), device=dev, dtype=th.float32)
+    t_end = th.empty_like(t_start)
+    counts = th.empty((B, Sc), device=dev, dtype=th.int32) if want_counts else None
+    flag = th.zeros((1,), device=dev, dtype=th.int32)
+    if fallback_u is not None:
+        fallback_u = _f32(fallback_u.reshape(-1), "fallback_u", (B,))
+    with th.cuda.device(dev):
+        check(lib().nerfb200_resample_alloc(_ptr(t_coarse), _ptr(weights), _ptr(delta_coarse), B, Sc,
+                                            n_samples, float(far), _ptr(t_start), _ptr(t_end),
+                                            _ptr(counts), _ptr(flag), _stream()), "resample_alloc")
+        check(lib().nerfb200_resample_fallback(_ptr(flag), float(near), float(far), B, n_samples,
+                                               _ptr(fallback_u), _ptr(t_start), _ptr(t_end),
+                                               _stream()), "resample_fallback")
+    if want_counts:
+        return t_start, t_end, counts, flag
+    return t_start, t_end
+
+
+# ---------------------------------------------------------------------------------------------
+# a12 inverse-CDF resampling
+# ---------------------------------------------------------------------------------------------
+def resample_icdf(edges, cdf, n_out: int, u_ray: Optional[th.Tensor] = None, want_idx: bool = False):
+    B, E = edges.shape
+    edges = _f32(edges.detach(), "edges", (B, E))
+    cdf = _f32(cdf.detach(), "cdf", (B, E))
+    if u_ray is not None:
+        u_ray = _f32(u_ray.reshape(-1), "u_ray", (B,))
+    out = th.empty((B, n_out + 1), device=edges.device, dtype=th.float32)
+    idx = th.empty((B, n_out), device=edges.device, dtype=th.int32) if want_idx else None
+    with th.cuda.device(edges.device):
+        check(lib().nerfb200_resample_icdf(_ptr(edges), _ptr(cdf), _ptr(u_ray), B, E - 1, n_out,
+                                           _ptr(out), _ptr(idx), _stream()), "resample_icdf")
+    return (out, idx) if want_idx else out
+
+
+# ---------------------------------------------------------------------------------------------
+# a13 camera extrinsics
+# ---------------------------------------------------------------------------------------------
+def so3_to_SO3(so3: th.Tensor) -> th.Tensor:
+    flat = _f32(so3.reshape(-1, 3), "so3")
+    out = th.empty((flat.shape[0], 3, 3), device=flat.device, dtype=th.float32)
+    with th.cuda.device(flat.device):
+        check(lib().nerfb200_so3_to_SO3(_ptr(flat), flat.shape[0], _ptr(out), _stream()), "so3_to_SO3")
+    return out
+
+
+class _Pose(th.autograd.Function):
+    """(o', d', R, t) = CameraExtrinsics.forward(i, o, d) — barf/model_camera_extrinsics.py:77-85.
+    Gradients flow to rotation / translation (and to o, d for completeness); R and t outputs
+    are returned detached, as nothing in the reference differentiates through them."""
+
+    @staticmethod
+    def forward(ctx, rotation, translation, img_idx, o, d):
+        B = o.shape[0]
+        rotation = _f32(rotation, "rotation")
+        translation = _f32(translation, "translation")
+        idx = _i32(img_idx, "img_idx")
+        o = _f32(o, "o", (B, 3))
+        d = _f32(d, "d", (B, 3))
+        out_o = th.empty_like(o)
+        out_d = th.empty_like(d)
+        out_R = th.empty((B, 3, 3), device=o.device, dtype=th.float32)
+        out_t = th.empty_like(o)
+        with th.cuda.device(o.device):
+            check(lib().nerfb200_pose_fwd(_ptr(rotation), _ptr(translation), _ptr(idx), _ptr(o), _ptr(d),
+                                          B, rotation.shape[0], _ptr(out_o), _ptr(out_d), _ptr(out_R),
+                                          _ptr(out_t), _stream()), "pose_fwd")
+        ctx.save_for_backward(rotation.detach(), idx, d.detach(), out_R)
+        ctx.mark_non_differentiable(out_R, out_t)
+        return out_o, out_d, out_R, out_t
+
+    @staticmethod
+    def backward(ctx, g_o, g_d, _gR, _gt):
+        rotation, idx, d, R = ctx.saved_tensors
+        B = d.shape[0]
+        g_o = th.zeros_like(d) if g_o is None else g_o.contiguous()
+        g_d = th.zeros_like(d) if g_d is None else g_d.contiguous()
+        d_rot = th.zeros_like(rotation)
+        d_tr = th.zeros_like(rotation)
+        with th.cuda.device(d.device):
+            check(lib().nerfb200_pose_bwd(_ptr(rotation), _ptr(idx), _ptr(d), _ptr(g_o), _ptr(g_d), B,
+                                          rotation.shape[0], _ptr(d_rot), _ptr(d_tr), _stream()),
+                  "pose_bwd")
+        g_in_d = th.matmul(R.transpose(1, 2), g_d.unsqueeze(-1)).squeeze(-1) if ctx.needs_input_grad[4] else None
+        return d_rot, d_tr, None, (g_o if ctx.needs_input_grad[3] else None), g_in_d
+
+
+def pose_forward(rotation, translation, img_idx, o, d):
+    return _Pose.apply(rotation, translation, img_idx, o, d)
