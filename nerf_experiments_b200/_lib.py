@@ -72,6 +72,13 @@ class NbPackBias(C.Structure):
                 ("dst_off", C.c_int32), ("reserved", C.c_int32)]
 
 
+class NbWgradItem(C.Structure):
+    _fields_ = [("tile_begin", C.c_int32), ("tile_end", C.c_int32), ("n_dy_slabs", C.c_int32),
+                ("n_x_slabs", C.c_int32), ("dy_slab", C.c_int32), ("x_slab", C.c_int32),
+                ("m_real", C.c_int32), ("n_real", C.c_int32), ("dst", C.c_int64), ("ld", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
 _lib = None
 
 
@@ -114,6 +121,10 @@ def _declare(L):
     L.nerfb200_mlp_pack.argtypes = [vp, vp, i32, vp, vp, i32, vp, vp]
     L.nerfb200_mlp_fwd.argtypes = [vp, vp, vp, C.POINTER(NbMlpInputs), C.POINTER(NbPeCfg),
                                    C.POINTER(NbPeCfg), vp, vp, f32, vp, vp, vp, vp, vp]
+    L.nerfb200_mlp_bwd.argtypes = [vp, vp, C.POINTER(NbMlpInputs), C.POINTER(NbPeCfg), C.POINTER(NbPeCfg),
+                                   vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, i32, i32, vp, vp, vp, vp,
+                                   i32, i32, vp, vp, vp]
+    L.nerfb200_mlp_wgrad.argtypes = [vp, i32, vp, i32, vp, i32, vp, vp]
     L.nerfb200_pe_fwd.argtypes = [C.POINTER(NbPeCfg), vp, vp, vp, vp, vp, vp, C.c_longlong, vp, vp]
     L.nerfb200_pe_bwd.argtypes = [C.POINTER(NbPeCfg), vp, vp, vp, vp, vp, vp, vp, C.c_longlong, vp, vp, vp]
     for name in EXPORTS:
@@ -128,7 +139,7 @@ EXPORTS = [
     "nerfb200_sample_uniform", "nerfb200_composite_fwd", "nerfb200_composite_bwd",
     "nerfb200_resample_alloc", "nerfb200_resample_fallback", "nerfb200_resample_icdf",
     "nerfb200_pose_fwd", "nerfb200_pose_bwd", "nerfb200_so3_to_SO3",
-    "nerfb200_mlp_pack", "nerfb200_mlp_fwd", "nerfb200_pe_fwd", "nerfb200_pe_bwd",
+    "nerfb200_mlp_pack", "nerfb200_mlp_fwd", "nerfb200_mlp_bwd", "nerfb200_mlp_wgrad", "nerfb200_pe_fwd", "nerfb200_pe_bwd",
 ]
 
 

@@ -127,6 +127,19 @@ typedef struct {
   int32_t reserved;
 } NbPackBias;
 
+/* One work item of the weight-gradient kernel: dW[m0:m0+m_real, c0:c0+n_real] +=
+ * dY[tiles, dy slabs]^T X[tiles, x slabs] over the tile range [tile_begin, tile_end). */
+typedef struct {
+  int32_t tile_begin, tile_end;
+  int32_t n_dy_slabs;           /* 1..4 consecutive dY stash slabs (64 output features each)  */
+  int32_t n_x_slabs;            /* 1..4 consecutive X stash slabs (64 input columns each)     */
+  int32_t dy_slab, x_slab;      /* first slab inside a tile's dY / X stash                    */
+  int32_t m_real, n_real;       /* real output features / input columns covered               */
+  int64_t dst;                  /* float index of dW[m0, c0] in the flat gradient buffer      */
+  int32_t ld;                   /* row stride of W (= in_features)                            */
+  int32_t reserved;
+} NbWgradItem;
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,7 +19,9 @@ struct MlpSmem {
   static constexpr uint32_t kSlabsOff = 0;
   static constexpr uint32_t kRingOff = NB_N_SLABS * NB_SLAB_BYTES;
   static constexpr uint32_t kCtrlOff = kRingOff + NB_RING_STAGES * NB_RING_STAGE_BYTES;
-  static constexpr uint32_t kBytes = kCtrlOff + 512;
+  static constexpr uint32_t kFloatsOff = kCtrlOff + 512;
+  static constexpr uint32_t kMaxBiasFloats = 4096;   // packed bias slots of one network
+  static constexpr uint32_t kBytes = kFloatsOff + kMaxBiasFloats * 4;
 
   uint8_t* base;
   uint64_t* full;      // [NB_RING_STAGES]
@@ -29,6 +31,7 @@ struct MlpSmem {
   uint32_t* tmem_ptr;
   float* mask_pos;     // [kMaxLevels]
   float* mask_dir;     // [kMaxLevels]
+  float* floats;       // [kMaxBiasFloats] bias-gradient accumulators (backward)
 
   __device__ explicit MlpSmem(uint8_t* b) : base(b) {
     uint8_t* c = b + kCtrlOff;
@@ -39,6 +42,7 @@ struct MlpSmem {
     tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
     mask_pos = reinterpret_cast<float*>(c + 128);
     mask_dir = mask_pos + kMaxLevels;
+    floats = reinterpret_cast<float*>(b + kFloatsOff);
   }
   __device__ uint8_t* slab(int i) const { return base + kSlabsOff + (uint32_t)i * NB_SLAB_BYTES; }
   __device__ uint8_t* ring(int s) const { return base + kRingOff + (uint32_t)s * NB_RING_STAGE_BYTES; }
@@ -106,6 +110,22 @@ __device__ __forceinline__ void encode_to_slab(const NbPeCfg& cfg, const float* 
     *reinterpret_cast<__nv_bfloat16*>(slab + tc::slab_offset((uint32_t)row, (uint32_t)col)) =
         __float2bfloat16_rn(v);
   });
+}
+
+// Column sums over the 32 lanes of a warp: lane i holds v[0..31] (one matrix row); on return
+// lane i holds sum over lanes of v[i]. 31 shuffles (recursive halving), v is destroyed.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool upper = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = upper ? v[i] : v[i + s];
+      const float keep = upper ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
 }
 
 // Range checks of a program before it reaches a kernel.

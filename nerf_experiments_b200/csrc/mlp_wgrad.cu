@@ -1,0 +1,192 @@
+// Weight gradients of the fused MLP on sm_100a: dW_l = dY_l^T X_l as tcgen05 MMAs whose K
+// dimension is the sample index. Both operands are the bf16 slabs the forward (X) and backward
+// (dY) kernels left in HBM; because a slab row is one sample, the very same bytes are valid
+// MN-major UMMA operands (tc.cuh), so they stream in by cp.async.bulk with no transposition.
+//
+// Work item = (layer, input source, <=2 blocks of 128 output features) x a range of tiles.
+// A persistent CTA accumulates its range in TMEM (2 x 256 fp32 columns) and flushes once with
+// red.global.add into the flat fp32 gradient buffer. HBM-bound by construction
+// (128 FLOP per byte of stash read).
+#include "common.cuh"
+#include "mlp.h"
+#include "tc.cuh"
+
+namespace nerfb200 {
+namespace {
+
+using namespace tc;
+
+constexpr int kWgThreads = 192;
+constexpr int kWgStages = 3;
+constexpr int kHalfRows = 64;                         // samples per pipeline stage
+constexpr uint32_t kHalfSlabBytes = kHalfRows * 128;  // 8 KB
+constexpr uint32_t kStageBytes = 8 * kHalfSlabBytes;  // up to 4 dY + 4 X half slabs
+constexpr uint32_t kWgSmemBytes = kWgStages * kStageBytes + 256;
+
+struct WgradParams {
+  const NbWgradItem* items;
+  int n_items;
+  int* counter;                 // dynamic work distribution (zeroed by the host wrapper)
+  const uint8_t* x_stash;
+  const uint8_t* dy_stash;
+  int x_slabs_per_tile, dy_slabs_per_tile;
+  float* d_params;
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+mlp_wgrad_kernel(const __grid_constant__ WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kWgStages * kStageBytes);
+  uint64_t* empty = full + kWgStages;
+  uint64_t* acc_full = empty + kWgStages;
+  uint64_t* acc_empty = acc_full + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 1);
+  int* next_item = reinterpret_cast<int*>(tmem_ptr + 1);   // [2] double-buffered broadcast slot
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWgStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 128);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_ptr, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // Static round-robin over items sorted by cost (host side): item = blockIdx.x + i*gridDim.x.
+  if (warp == 5) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
+        const NbWgradItem item = p.items[it];
+        const uint32_t bytes = (uint32_t)(item.n_dy_slabs + item.n_x_slabs) * kHalfSlabBytes;
+        for (int tile = item.tile_begin; tile < item.tile_end; ++tile) {
+          const uint8_t* dy = p.dy_stash + ((size_t)tile * p.dy_slabs_per_tile + item.dy_slab) * NB_SLAB_BYTES;
+          const uint8_t* x = p.x_stash + ((size_t)tile * p.x_slabs_per_tile + item.x_slab) * NB_SLAB_BYTES;
+          for (int half = 0; half < 2; ++half) {
+            mbar_wait(&empty[stage], phase ^ 1u);
+            mbar_arrive_expect_tx(&full[stage], bytes);
+            uint8_t* dst = smem + stage * kStageBytes;
+            for (int s = 0; s < item.n_dy_slabs; ++s)
+              bulk_g2s(dst + s * kHalfSlabBytes, dy + (size_t)s * NB_SLAB_BYTES + half * kHalfSlabBytes,
+                       kHalfSlabBytes, &full[stage]);
+            for (int s = 0; s < item.n_x_slabs; ++s)
+              bulk_g2s(dst + (4 + s) * kHalfSlabBytes, x + (size_t)s * NB_SLAB_BYTES + half * kHalfSlabBytes,
+                       kHalfSlabBytes, &full[stage]);
+            if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 4) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, e_phase = 0;
+      bool first_item = true;
+      for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
+        const NbWgradItem item = p.items[it];
+        const int n_mb = (item.n_dy_slabs + 1) / 2;
+        const uint32_t idesc = umma_idesc(128, item.n_x_slabs * 64, true, true);
+        if (!first_item) {   // the flush of the previous item must have drained TMEM
+          mbar_wait(acc_empty, e_phase);
+          e_phase ^= 1u;
+          tcgen05_fence_after();
+        }
+        first_item = false;
+        uint32_t acc = 0;
+        for (int tile = item.tile_begin; tile < item.tile_end; ++tile) {
+          for (int half = 0; half < 2; ++half) {
+            mbar_wait(&full[stage], phase);
+            tcgen05_fence_after();
+            const uint32_t base = smem_u32(smem + stage * kStageBytes);
+            for (int k = 0; k < kHalfRows / 16; ++k) {
+              const uint64_t bdesc = umma_desc_mnmajor(base + 4 * kHalfSlabBytes, kHalfSlabBytes, k);
+              for (int mb = 0; mb < n_mb; ++mb) {
+                const uint64_t adesc = umma_desc_mnmajor(base + mb * 2 * kHalfSlabBytes, kHalfSlabBytes, k);
+                umma(tmem_base + (uint32_t)(mb * 256), adesc, bdesc, idesc, acc);
+              }
+              acc = 1;
+            }
+            umma_commit(&empty[stage]);
+            if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+        umma_commit(acc_full);
+      }
+    }
+  } else {
+    // flush warps: TMEM lane = output feature within the 128-block
+    uint32_t f_phase = 0;
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
+      const NbWgradItem item = p.items[it];
+      const int n_mb = (item.n_dy_slabs + 1) / 2;
+      mbar_wait(acc_full, f_phase);
+      f_phase ^= 1u;
+      tcgen05_fence_after();
+      if (item.tile_end > item.tile_begin) {
+        for (int mb = 0; mb < n_mb; ++mb) {
+          const int m = mb * 128 + threadIdx.x;
+          // whole warps skip together: tcgen05.ld is warp-collective
+          const bool warp_has_rows = (mb * 128 + warp * 32) < item.m_real;
+          if (!warp_has_rows) continue;
+          float* dst_row = p.d_params + item.dst + (long long)m * item.ld;
+          for (int g = 0; g < item.n_real; g += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_lane + (uint32_t)(mb * 256 + g), v);
+            tmem_ld_wait();
+            if (m < item.m_real) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (g + i < item.n_real) atomicAdd(dst_row + g + i, __uint_as_float(v[i]));
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(acc_empty);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+}  // namespace nerfb200
+
+using namespace nerfb200;
+
+extern "C" int nerfb200_mlp_wgrad(const NbWgradItem* items_dev, int n_items, const void* x_stash,
+                                  int x_slabs_per_tile, const void* dy_stash,
+                                  int dy_slabs_per_tile, float* d_params, void* stream) {
+  NB_CHECK_ARG(n_items >= 0 && (n_items == 0 || (items_dev && x_stash && dy_stash && d_params)),
+               "mlp_wgrad: bad arguments");
+  if (n_items == 0) return NERFB200_OK;
+  WgradParams p;
+  p.items = items_dev;
+  p.n_items = n_items;
+  p.counter = nullptr;
+  p.x_stash = reinterpret_cast<const uint8_t*>(x_stash);
+  p.dy_stash = reinterpret_cast<const uint8_t*>(dy_stash);
+  p.x_slabs_per_tile = x_slabs_per_tile;
+  p.dy_slabs_per_tile = dy_slabs_per_tile;
+  p.d_params = d_params;
+  static bool configured = false;
+  if (!configured) {
+    NB_CHECK_CUDA(cudaFuncSetAttribute(mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)kWgSmemBytes));
+    configured = true;
+  }
+  const int grid = n_items < sm_count() ? n_items : sm_count();
+  mlp_wgrad_kernel<<<grid, kWgThreads, kWgSmemBytes, (cudaStream_t)stream>>>(p);
+  count_launch();
+  NB_CHECK_LAUNCH();
+  return NERFB200_OK;
+}

@@ -11,6 +11,7 @@
 namespace nerfb200 {
 
 constexpr int kMaxLevels = 16;
+constexpr int kPeAnchor = 4;   // levels between exact sincos evaluations (error <= ~2e-6)
 
 // BARF coarse-to-fine mask (positional_encodings.py:105-122) from the alpha buffer.
 __device__ __forceinline__ void pe_fill_mask(const NbPeCfg& cfg, const float* alpha_ptr,
@@ -88,10 +89,12 @@ __device__ __forceinline__ void pe_encode(const NbPeCfg& cfg, const float* mask,
   const int L = cfg.levels;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    float sn, cs;
-    sincosf(x[c] * cfg.scale, &sn, &cs);
+    float sn = 0.f, cs = 1.f;
     float lvl = 1.f;  // 4^j
+    float freq = cfg.scale;
     for (int j = 0; j < L; ++j) {
+      // exact evaluation every kPeAnchor levels, double-angle steps in between
+      if ((j % kPeAnchor) == 0) sincosf(x[c] * freq, &sn, &cs);
       float w = mask[j];
       if (cfg.kind == NB_PE_INTEGRATED) w *= __expf(-0.5f * ipe.var[c] * lvl);
       emit(col + c * L + j, w * cs);
@@ -101,6 +104,7 @@ __device__ __forceinline__ void pe_encode(const NbPeCfg& cfg, const float* mask,
       cs = 1.f - 2.f * sn * sn;
       sn = s2;
       lvl *= 4.f;
+      freq *= 2.f;
     }
   }
 }
@@ -131,11 +135,11 @@ __device__ __forceinline__ void pe_backward(const NbPeCfg& cfg, const float* mas
   const int L = cfg.levels;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    float sn, cs;
-    sincosf(x[c] * cfg.scale, &sn, &cs);
+    float sn = 0.f, cs = 1.f;
     float lvl = 1.f, freq = cfg.scale;
     float acc = 0.f;
     for (int j = 0; j < L; ++j) {
+      if ((j % kPeAnchor) == 0) sincosf(x[c] * freq, &sn, &cs);
       float w = mask[j];
       if (cfg.kind == NB_PE_INTEGRATED) w *= __expf(-0.5f * ipe.var[c] * lvl);
       acc += w * freq * (cs * g(col + 3 * L + c * L + j) - sn * g(col + c * L + j));

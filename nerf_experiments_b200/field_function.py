@@ -28,7 +28,7 @@ class _FieldFunction(th.autograd.Function):
             raise RuntimeError("the fused field runs on CUDA only (nerfb200 has no CPU fallback)")
         field = model.fused_field()
         field.prepare(dev)
-        training = th.is_grad_enabled() and (any(p.requires_grad for p in params) or a.requires_grad or b.requires_grad)
+        training = any(ctx.needs_input_grad)   # grad mode is off inside Function.forward
         if mode == "samples":
             n = a.shape[0]
             inputs = make_inputs(n, 1, 0, pos=a, dir=b, t_start=t_start, t_end=t_end,

@@ -10,8 +10,9 @@ import torch.nn as nn
 
 from . import _lib
 from ._lib import NbMlpInputs, NbPackBias, NbPackChunk, check, lib
-from .mlp_program import (SLAB_PE_DIR, SLAB_PE_POS, CompiledMlp, LayerSpec, Linear, compile_forward,
-                          to_device_array)
+from ._lib import NbWgradItem
+from .mlp_program import (SLAB_PE_DIR, SLAB_PE_POS, CompiledMlp, LayerSpec, Linear, compile_backward,
+                          compile_forward, schedule_wgrad, to_device_array)
 
 
 def _ptr(t):
@@ -84,16 +85,36 @@ class FusedField:
             self.compiled = compile_forward(self.layers_fn(self.flat))
             cm = self.compiled
             self.device = device
-            self.wpack = th.empty(max(cm.wpack_bytes, 1024), device=device, dtype=th.uint8)
+            # backward programs: [False] weights only, [True] also gradients w.r.t. the inputs.
+            # Their transposed weight images follow the forward images in one packed buffer.
+            self.bwd = {}
+            all_chunks = list(cm.pack_chunks)
+            units = cm.wpack_bytes // 1024
+            for want in (False, True):
+                cb = compile_backward(cm, want)
+                shift = units - cm.wpack_bytes // 1024
+                for ch in cb.pack_chunks:
+                    ch.dst_off += shift
+                for i in range(cb.program.n_ops):
+                    op = cb.program.ops[i]
+                    for c in range(op.n_chunks):
+                        op.w_off[c] += shift
+                units += cb.wpack_units
+                all_chunks += cb.pack_chunks
+                self.bwd[want] = cb
+            self.n_pack_chunks = len(all_chunks)
+            self.wpack = th.empty(max(units * 1024, 1024), device=device, dtype=th.uint8)
             self.bias = th.zeros(max(cm.bias_floats, 1), device=device, dtype=th.float32)
-            self.chunks_dev = to_device_array(cm.pack_chunks, NbPackChunk, device)
+            self.chunks_dev = to_device_array(all_chunks, NbPackChunk, device)
             self.biases_dev = to_device_array(cm.pack_biases, NbPackBias, device)
+            self.bias_map_dev = th.tensor(self.bwd[False].bias_map or [-1], device=device, dtype=th.int32)
+            self._wgrad_items = {}
             self._packed_sig = None
         sig = self.flat.signature()
         if sig != self._packed_sig:
             cm = self.compiled
             with th.cuda.device(device):
-                check(lib().nerfb200_mlp_pack(_ptr(flat), _ptr(self.chunks_dev), len(cm.pack_chunks),
+                check(lib().nerfb200_mlp_pack(_ptr(flat), _ptr(self.chunks_dev), self.n_pack_chunks,
                                               _ptr(self.wpack), _ptr(self.biases_dev), len(cm.pack_biases),
                                               _ptr(self.bias), th.cuda.current_stream().cuda_stream),
                       "mlp_pack")
@@ -129,6 +150,51 @@ class FusedField:
                                          float(self.sigma_bias), _ptr(sigma), _ptr(rgb), _ptr(stash),
                                          _ptr(masks), th.cuda.current_stream().cuda_stream), "mlp_fwd")
         return sigma, rgb, stash, masks
+
+
+    def _items(self, n_tiles: int):
+        if n_tiles not in self._wgrad_items:
+            n_sm = th.cuda.get_device_properties(self.device).multi_processor_count
+            items = schedule_wgrad(self.bwd[False].units, n_tiles, n_sm)
+            self._wgrad_items[n_tiles] = (to_device_array(items, NbWgradItem, self.device), len(items))
+        return self._wgrad_items[n_tiles]
+
+    def backward(self, inputs: NbMlpInputs, n: int, sigma, rgb, g_sigma, g_rgb, stash, masks,
+                 want_input_grads: bool, n_rays: int):
+        """Backward of `forward`: returns the flat fp32 parameter-gradient buffer and the input
+        gradients ((d_o, d_d) per ray in rays mode, (d_pos, d_dir) per sample otherwise)."""
+        dev = self.device
+        cm = self.compiled
+        cb = self.bwd[bool(want_input_grads)]
+        n_tiles = (n + _lib.NB_TILE_ROWS - 1) // _lib.NB_TILE_ROWS
+        dy_stash = th.empty(n_tiles * cb.dy_slabs_per_tile * _lib.NB_SLAB_BYTES, device=dev, dtype=th.uint8)
+        flat_grad = th.zeros(self.flat.numel, device=dev, dtype=th.float32)
+        d_a = d_b = None
+        samples_mode = bool(inputs.pos)
+        if want_input_grads:
+            if samples_mode:
+                d_a = th.empty((n, 3), device=dev, dtype=th.float32)
+                d_b = th.empty((n, 3), device=dev, dtype=th.float32)
+            else:
+                d_a = th.zeros((n_rays, 3), device=dev, dtype=th.float32)
+                d_b = th.zeros((n_rays, 3), device=dev, dtype=th.float32)
+        cp, cd = self.pe_cfgs()
+        stream = th.cuda.current_stream().cuda_stream
+        with th.cuda.device(dev):
+            check(lib().nerfb200_mlp_bwd(
+                C.byref(cb.program), _ptr(self.wpack), C.byref(inputs), C.byref(cp), C.byref(cd),
+                _ptr(self.pe_pos.alpha_tensor()), _ptr(self.pe_dir.alpha_tensor()), _ptr(sigma), _ptr(rgb),
+                _ptr(g_sigma), _ptr(g_rgb), _ptr(masks), cm.mask_words_per_tile, _ptr(dy_stash),
+                cb.head_sigma_col3, cb.pos_grad_cols if want_input_grads else 0,
+                cb.dir_grad_cols if want_input_grads else 0,
+                None if samples_mode else _ptr(d_a), None if samples_mode else _ptr(d_b),
+                _ptr(d_a) if samples_mode else None, _ptr(d_b) if samples_mode else None,
+                cb.head_bias_off, cm.bias_floats, _ptr(self.bias_map_dev), _ptr(flat_grad), stream), "mlp_bwd")
+            items_dev, n_items = self._items(n_tiles)
+            check(lib().nerfb200_mlp_wgrad(_ptr(items_dev), n_items, _ptr(stash), cm.stash_slabs_per_tile,
+                                           _ptr(dy_stash), cb.dy_slabs_per_tile, _ptr(flat_grad), stream),
+                  "mlp_wgrad")
+        return flat_grad, d_a, d_b
 
 
 def make_inputs(n: int, S: int, t_mode: int, ray_o=None, ray_d=None, t_start=None, t_end=None,

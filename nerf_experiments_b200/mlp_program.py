@@ -210,3 +210,187 @@ def to_device_array(items, ctype, device):
     buf = bytes(arr)[: n * C.sizeof(ctype)] if n else b""
     t = th.frombuffer(bytearray(buf if buf else b"\0"), dtype=th.uint8).clone()
     return t.to(device)
+
+
+# ---------------------------------------------------------------------------------------------
+# backward (data gradients) and weight-gradient schedules
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class WgradUnit:
+    dy_slab: int
+    n_dy_slabs: int
+    x_slab: int
+    n_x_slabs: int
+    m_real: int
+    n_real: int
+    dst: int
+    ld: int
+
+
+@dataclass
+class CompiledBackward:
+    program: NbProgram
+    pack_chunks: List[NbPackChunk]
+    wpack_units: int                  # 1024 B units appended to the packed weight buffer
+    dy_slabs_per_tile: int
+    head_bias_off: int
+    head_sigma_col3: int
+    pos_grad_cols: int
+    dir_grad_cols: int
+    bias_map: List[int]
+    units: List[WgradUnit]
+
+
+def _out_chunks(L: LayerSpec) -> int:
+    return 0 if L.act == "rgb" else _ceil(L.out_main, 64)
+
+
+def compile_backward(cm: CompiledMlp, want_input_grads: bool) -> CompiledBackward:
+    layers = cm.layers
+    n_layers = len(layers)
+    fprog = cm.program
+    w_units = cm.wpack_bytes // 1024
+    w_units0 = w_units
+    chunks: List[NbPackChunk] = []
+
+    # dY stash: slab 0 = head; then dY_{l-1} in the order the backward ops create them
+    dy_slab = {n_layers - 1: 0}
+    nxt = 1
+    for l in range(n_layers - 1, 0, -1):
+        prev = layers[l - 1]
+        dy_slab[l - 1] = nxt
+        nxt += _out_chunks(prev) + (1 if prev.sigma == "extra" else 0)
+    dy_slabs_per_tile = nxt
+
+    prog = NbProgram()
+    ops = []
+    seen = {"pos": 0, "dir": 0}
+    grad_cols = {"pos": 0, "dir": 0}
+    for l in range(n_layers - 1, -1, -1):
+        L = layers[l]
+        lin = L.lin
+        # A operand: dY_l
+        if L.act == "rgb":
+            a_chunks = [(0, 1, 0, lin.out_f)]            # (slab, k16, first out row, n out rows)
+        else:
+            a_chunks = []
+            for c in range(_out_chunks(L)):
+                w = min(64, L.out_main - 64 * c)
+                a_chunks.append((c, _ceil(w, 16), 64 * c, w))
+            if L.sigma == "extra":
+                a_chunks.append((4, 1, L.out_main, 1))
+        col0 = 0
+        main_src = None
+        aux_srcs = []
+        for src in L.sources:
+            if src.kind == "act":
+                main_src = (col0, src.width)
+            else:
+                aux_srcs.append((src.kind, col0, src.width))
+            col0 += src.width
+
+        def emit(op: NbOp, col_first: int, width: int, n_block: int, tmem_col: int, accum: int):
+            nonlocal w_units
+            op.n_chunks = len(a_chunks)
+            for ci, (slab, k16, krow0, kcols) in enumerate(a_chunks):
+                op.a_src[ci] = slab
+                op.k16[ci] = k16
+                op.w_rows[ci] = n_block
+                op.w_off[ci] = w_units
+                chunks.append(NbPackChunk(base=lin.w_off + krow0 * lin.in_f + col_first, row_stride=1,
+                                          col_stride=lin.in_f, n_rows=width, n_cols=kcols,
+                                          rows_padded=n_block, dst_off=w_units))
+                w_units += n_block // 8
+            op.n_blocks = 1
+            op.blocks[0] = NbBlock(tmem_col, n_block, 0, accum)
+
+        if want_input_grads:
+            for kind, c0, width in aux_srcs:
+                op = NbOp()
+                n_block = _ceil(width, 32) * 32
+                emit(op, c0, width, n_block, TMEM_EXTRA_COL if kind == "pos" else TMEM_DIR_COL, seen[kind])
+                seen[kind] = 1
+                grad_cols[kind] = max(grad_cols[kind], n_block)
+                op.epi = _lib.BEPI_NONE
+                op.out_chunks = 0
+                op.bias_off = -1
+                op.stash_slab = -1
+                op.mask_word = -1
+                ops.append(op)
+        if main_src is not None:
+            if l == 0:
+                raise RuntimeError("first layer cannot take activations")
+            prev = layers[l - 1]
+            c0, width = main_src
+            op = NbOp()
+            emit(op, c0, width, _ceil(width, 64) * 64, 0, 0)
+            relu = (prev.act == "relu")
+            sig = (prev.sigma == "extra")
+            op.epi = {(True, False): _lib.BEPI_MASK, (False, False): _lib.BEPI_PLAIN,
+                      (False, True): _lib.BEPI_PLAIN_SIGMA, (True, True): _lib.BEPI_MASK_SIGMA}[(relu, sig)]
+            op.out_chunks = _ceil(width, 64)
+            op.bias_off = fprog.ops[l - 1].bias_off
+            op.stash_slab = dy_slab[l - 1]
+            op.mask_word = fprog.ops[l - 1].mask_word if relu else -1
+            op.out_width = width
+            ops.append(op)
+    if len(ops) > NB_MAX_OPS:
+        raise RuntimeError("backward program too long")
+    prog.n_ops = len(ops)
+    for i, op in enumerate(ops):
+        prog.ops[i] = op
+    prog.stash_slabs_per_tile = dy_slabs_per_tile
+    prog.mask_words_per_tile = cm.mask_words_per_tile
+
+    bias_map = [-1] * cm.bias_floats
+    for pb in cm.pack_biases:
+        for i in range(pb.n):
+            bias_map[pb.dst_off + i] = pb.base + i
+
+    # weight-gradient units
+    units: List[WgradUnit] = []
+    for l, L in enumerate(layers):
+        lin = L.lin
+        n_main_slabs = 1 if L.act == "rgb" else _out_chunks(L)
+        m_main = lin.out_f if L.act == "rgb" else L.out_main
+        col0 = 0
+        for src in L.sources:
+            if src.kind == "act":
+                x_slab, n_x = fprog.ops[l - 1].stash_slab, _ceil(src.width, 64)
+            else:
+                x_slab, n_x = (0 if src.kind == "pos" else 1), 1
+            units.append(WgradUnit(dy_slab[l], n_main_slabs, x_slab, n_x, m_main, src.width,
+                                   lin.w_off + col0, lin.in_f))
+            if L.sigma == "extra":
+                units.append(WgradUnit(dy_slab[l] + n_main_slabs, 1, x_slab, n_x, 1, src.width,
+                                       lin.w_off + L.out_main * lin.in_f + col0, lin.in_f))
+            col0 += src.width
+
+    head = layers[-1]
+    return CompiledBackward(program=prog, pack_chunks=chunks, wpack_units=w_units - w_units0,
+                            dy_slabs_per_tile=dy_slabs_per_tile, head_bias_off=fprog.ops[n_layers - 1].bias_off,
+                            head_sigma_col3=1 if head.sigma == "col3" else 0,
+                            pos_grad_cols=grad_cols["pos"], dir_grad_cols=grad_cols["dir"],
+                            bias_map=bias_map, units=units)
+
+
+def schedule_wgrad(units: List[WgradUnit], n_tiles: int, n_workers: int):
+    """Splits every unit over tile ranges so that ~2 items per worker of similar cost result;
+    returns NbWgradItem structs sorted by decreasing cost (static round-robin in the kernel)."""
+    from ._lib import NbWgradItem
+    cost = [(u.n_dy_slabs + u.n_x_slabs) for u in units]
+    total = sum(cost) * n_tiles
+    target = max(total / max(2 * n_workers, 1), 1.0)
+    items = []
+    for u, c in zip(units, cost):
+        splits = int(min(n_tiles, max(1, round(c * n_tiles / target))))
+        for s in range(splits):
+            t0 = (n_tiles * s) // splits
+            t1 = (n_tiles * (s + 1)) // splits
+            if t1 > t0:
+                items.append((c * (t1 - t0), NbWgradItem(tile_begin=t0, tile_end=t1, n_dy_slabs=u.n_dy_slabs,
+                                                         n_x_slabs=u.n_x_slabs, dy_slab=u.dy_slab, x_slab=u.x_slab,
+                                                         m_real=u.m_real, n_real=u.n_real, dst=u.dst, ld=u.ld,
+                                                         reserved=0)))
+    items.sort(key=lambda t: -t[0])
+    return [it for _, it in items]
