@@ -19,6 +19,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include "nerfb200_mlp.h" /* tile-program structs passed across the ABI */
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -133,6 +135,77 @@ int nerfb200_pose_bwd(const float* rotation, const int32_t* img_idx, const float
 
 /* so3_to_SO3 alone (barf/model_camera_extrinsics.py:22-43): so3 (n,3) -> R (n,3,3). */
 int nerfb200_so3_to_SO3(const float* so3, int n, float* out_R, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stand-alone positional encodings (fp32 in/out); PeCfg is NbPeCfg of csrc/mlp.h.
+ * Replaces forward() of FourierFeatures / BarfPositionalEncoding / IntegratedFourierFeatures /
+ * IntegratedBarfFourierFeatures (barf/positional_encodings.py:43-57, :124-148, :170-240, :266-282).
+ *   pos, dir: (N,3); pixel_width, t_start, t_end: (N,) (integrated encoding only, else NULL)
+ *   alpha: device scalar of the BARF mask or NULL; out: (N, output_dim).
+ */
+int nerfb200_pe_fwd(const NbPeCfg* cfg_host, const float* alpha, const float* pos,
+                    const float* dir, const float* pixel_width, const float* t_start,
+                    const float* t_end, long long N, float* out, void* stream);
+int nerfb200_pe_bwd(const NbPeCfg* cfg_host, const float* alpha, const float* pos,
+                    const float* dir, const float* pixel_width, const float* t_start,
+                    const float* t_end, const float* g_out, long long N, float* d_pos,
+                    float* d_dir, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a2-a9. Fused field: query positions + positional encodings + radiance / proposal MLP.
+ * Replaces NerfInterpolation._compute_positions + NerfModel.forward and their autograd
+ * (barf/model_interpolation.py:288-312, barf/model_interpolation_architecture.py:96-141).
+ * The network is described by a tile program (NbProgram, csrc/mlp.h) compiled on the host; the
+ * structs are plain C and are passed from HOST memory.
+ *
+ * nerfb200_mlp_pack   refreshes the packed bf16 weight images / padded fp32 biases from the flat
+ *                     fp32 parameter buffer (once per optimiser step).
+ * nerfb200_mlp_fwd    sigma (N,), rgb (N,3). With stash/masks non-NULL (training) it also saves
+ *                     every layer input as bf16 slabs (stash: n_tiles * stash_slabs_per_tile *
+ *                     16 KiB) and the ReLU sign bits (masks: n_tiles * mask_words_per_tile * 128
+ *                     uint32).
+ * nerfb200_mlp_bwd    data gradients: walks the layers in reverse, writes every dY as bf16 slabs
+ *                     (dy_stash: n_tiles * program.stash_slabs_per_tile * 16 KiB), accumulates
+ *                     the bias gradients into d_params (+=) and, if pos_grad_cols/dir_grad_cols
+ *                     are non-zero, the gradients w.r.t. ray origins / directions (+=, caller
+ *                     zeroes) or per-sample positions / directions.
+ * nerfb200_mlp_wgrad  weight gradients dW += dY^T X over the work items (NbWgradItem, DEVICE
+ *                     array) into d_params.
+ */
+int nerfb200_mlp_pack(const float* params, const NbPackChunk* chunks_dev, int n_chunks,
+                      void* wpack, const NbPackBias* biases_dev, int n_biases,
+                      float* bias_out, void* stream);
+int nerfb200_mlp_fwd(const void* program_host, const void* wpack, const float* bias,
+                     const NbMlpInputs* in_host, const NbPeCfg* pe_pos_host,
+                     const NbPeCfg* pe_dir_host, const float* alpha_pos,
+                     const float* alpha_dir, float sigma_bias, float* out_sigma, float* out_rgb,
+                     void* stash, uint32_t* masks, void* stream);
+int nerfb200_mlp_bwd(const void* program_host, const void* wpack_t,
+                     const NbMlpInputs* in_host, const NbPeCfg* pe_pos_host,
+                     const NbPeCfg* pe_dir_host, const float* alpha_pos,
+                     const float* alpha_dir, const float* sigma, const float* rgb,
+                     const float* g_sigma, const float* g_rgb, const uint32_t* masks,
+                     int fwd_mask_words_per_tile, void* dy_stash, int head_sigma_col3,
+                     int pos_grad_cols, int dir_grad_cols, float* d_ray_o, float* d_ray_d,
+                     float* d_pos, float* d_dir, int head_bias_off, int n_bias_floats,
+                     const int32_t* bias_map, float* d_params, void* stream);
+int nerfb200_mlp_wgrad(const NbWgradItem* items_dev, int n_items, const void* x_stash,
+                       int x_slabs_per_tile, const void* dy_stash, int dy_slabs_per_tile,
+                       float* d_params, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K9. Fused Adam over the flat fp32 parameter buffer (torch.optim.Adam arithmetic, per-group
+ * learning rate / weight decay), replacing the optimiser the reference configures at
+ * barf/model_interpolation.py:543-564.  group_* are HOST arrays of n_groups entries
+ * ([begin,end) float ranges of the flat buffer); step counts from 1; grads are multiplied by
+ * grad_scale first (1/world_size after a sum all-reduce).
+ */
+#define NERFB200_MAX_ADAM_GROUPS 8
+int nerfb200_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                       long long n, int n_groups, const long long* group_begin_host,
+                       const long long* group_end_host, const float* group_lr_host,
+                       const float* group_wd_host, float beta1, float beta2, float eps,
+                       long long step, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,145 +1,3 @@
-// Tile-program description shared by the host side and the fused MLP kernels.
-//
-// A network is compiled (by the Python host mirror, nerf_experiments_b200/mlp_program.py) into
-// a short program of GEMM ops executed on one 128-sample tile that stays on-chip:
-//   A operand  = up to kMaxChunks 64-wide K chunks taken from shared-memory slabs
-//   B operand  = one packed bf16 weight image per K chunk, streamed from L2 by the TMA engine
-//   D          = up to kMaxBlocks N-blocks of the TMEM accumulator
-//   epilogue   = what the 128 row-threads do with D (activation, store as next A, outputs)
-// The same structure describes forward (A = activations, B = W) and backward-data
-// (A = dY, B = W^T) passes.
+// The tile-program structs are part of the C ABI: see include/nerfb200_mlp.h.
 #pragma once
-#include <stdint.h>
-
-#ifdef __cplusplus
-extern "C" {
-#endif
-
-enum {
-  NB_MAX_OPS = 40,
-  NB_MAX_CHUNKS = 6,
-  NB_MAX_BLOCKS = 3,
-  NB_TILE_ROWS = 128,
-  NB_SLAB_BYTES = 128 * 128,          /* 128 rows x 64 bf16 */
-  NB_N_SLABS = 6,                     /* 0..3 activations, 4 and 5 auxiliary (PE / extra) */
-  NB_RING_STAGE_BYTES = 272 * 128,    /* largest weight image: 272 rows x 64 bf16 */
-  NB_RING_STAGES = 3
-};
-
-/* forward epilogues */
-enum {
-  NB_EPI_RELU = 0,        /* y = relu(acc+b) -> act slabs                                      */
-  NB_EPI_LINEAR = 1,      /* y = acc+b -> act slabs                                            */
-  NB_EPI_LINEAR_SIGMA = 2,/* as LINEAR, and sigma = softplus8(extra block col 0 + b) -> out    */
-  NB_EPI_RGB = 3,         /* rgb = sigmoid(acc[0:3]+b) -> out                                  */
-  NB_EPI_RGB_SIGMA = 4,   /* as RGB, and sigma = softplus8(acc[3]+b[3]) -> out (delayed dens.) */
-  NB_EPI_RELU_SIGMA = 5   /* y = relu(acc+b) -> act slabs, sigma from extra block              */
-};
-
-/* backward (data-gradient) epilogues */
-enum {
-  NB_BEPI_MASK = 0,       /* dY_prev = acc * relu_mask(bits) -> act slabs (+dY stash)          */
-  NB_BEPI_PLAIN = 1,      /* dY_prev = acc -> act slabs (+dY stash)                            */
-  NB_BEPI_PLAIN_SIGMA = 2,/* as PLAIN and d(sigma_pre) -> aux slab 4 col 0                     */
-  NB_BEPI_MASK_SIGMA = 3, /* as MASK and d(sigma_pre) -> aux slab 4 col 0                      */
-  NB_BEPI_NONE = 4        /* nothing to store (only persistent PE-gradient blocks written)     */
-};
-
-typedef struct {
-  int16_t tmem_col;   /* first accumulator column                                             */
-  int16_t n;          /* MMA N (multiple of 16, <= 256)                                        */
-  int16_t row0;       /* first row of the weight image used as B (multiple of 8)               */
-  int16_t accum_in;   /* 1: accumulate onto what an earlier op left in these columns           */
-} NbBlock;
-
-typedef struct {
-  int8_t n_chunks;
-  int8_t n_blocks;
-  int8_t epi;
-  int8_t out_chunks;                 /* 64-wide slabs the epilogue writes (act slabs 0..)       */
-  int8_t a_src[NB_MAX_CHUNKS];       /* slab id of every K chunk                                */
-  int8_t k16[NB_MAX_CHUNKS];         /* 16-wide MMA K steps in every chunk (1..4)               */
-  int16_t w_rows[NB_MAX_CHUNKS];     /* rows of the weight image of every chunk                 */
-  int32_t w_off[NB_MAX_CHUNKS];      /* offset of the image in the packed buffer, 1024 B units  */
-  NbBlock blocks[NB_MAX_BLOCKS];
-  int32_t bias_off;                  /* float index into the packed bias buffer (-1: none)      */
-  int32_t stash_slab;                /* first stash slab (per tile) of the output, -1: none     */
-  int32_t mask_word;                 /* first mask word row-group (per tile), -1: none          */
-  int32_t out_width;                 /* real (unpadded) number of output features               */
-} NbOp;
-
-typedef struct {
-  int32_t n_ops;
-  int32_t stash_slabs_per_tile;      /* slabs of NB_SLAB_BYTES per tile in the stash            */
-  int32_t mask_words_per_tile;       /* 32-column groups per tile (x128 rows x 4 B)             */
-  int32_t reserved;
-  NbOp ops[NB_MAX_OPS];
-} NbProgram;
-
-/* positional encodings (reference barf/positional_encodings.py) */
-enum { NB_PE_IDENTITY = 0, NB_PE_FOURIER = 1, NB_PE_INTEGRATED = 2 };
-
-typedef struct {
-  int32_t kind;                 /* NB_PE_*                                                    */
-  int32_t levels;               /* L (0 allowed: identity only)                               */
-  int32_t include_identity;
-  int32_t use_mask;             /* BARF coarse-to-fine mask from *alpha                       */
-  int32_t distribute_variance;  /* integrated PE only                                         */
-  float scale;
-  float pixel_width_sigma;      /* integrated PE only                                         */
-  int32_t slab;                 /* destination slab id (4 or 5), -1: encoder unused           */
-  int32_t stash_slab;           /* stash slab (per tile) of the encoding, -1: none            */
-} NbPeCfg;
-
-/* Where the samples of a launch come from.  Either per-ray data (positions are computed in the
- * kernel: x = o + t_q d, reference barf/model_interpolation.py:279-312) or per-sample pos/dir
- * (the NerfModel.forward signature, barf/model_interpolation_architecture.py:96-104). */
-typedef struct {
-  int64_t N;                 /* samples = rays * S                                          */
-  int32_t S;                 /* samples per ray; ray index of sample n is n / S               */
-  int32_t t_mode;            /* 0: "left" (t_q = t_start), 1: "middle" ((t_start+t_end)/2)    */
-  const float* ray_o;        /* (B,3) used when pos == NULL                                   */
-  const float* ray_d;        /* (B,3)                                                         */
-  const float* t_start;      /* (N,) or NULL                                                  */
-  const float* t_end;        /* (N,) or NULL                                                  */
-  const float* pixel_width;  /* (B,) / (N,) or NULL                                           */
-  const float* pos;          /* (N,3) or NULL                                                 */
-  const float* dir;          /* (N,3) or NULL (with pos)                                      */
-  int32_t pixel_width_per_sample;
-  int32_t reserved;
-} NbMlpInputs;
-
-/* A packed weight image: image(r,c) = params[base + r*row_stride + c*col_stride] for
- * r < n_rows, c < n_cols, zero elsewhere; rows_padded rows of 64 bf16, swizzled slab layout. */
-typedef struct {
-  int64_t base;
-  int32_t row_stride, col_stride;
-  int32_t n_rows, n_cols;
-  int32_t rows_padded;
-  int32_t dst_off;              /* 1024 B units into the packed buffer                        */
-} NbPackChunk;
-
-/* A packed bias segment: dst[dst_off + i] = params[base + i] for i < n, 0 for n <= i < n_padded */
-typedef struct {
-  int64_t base;
-  int32_t n, n_padded;
-  int32_t dst_off;
-  int32_t reserved;
-} NbPackBias;
-
-/* One work item of the weight-gradient kernel: dW[m0:m0+m_real, c0:c0+n_real] +=
- * dY[tiles, dy slabs]^T X[tiles, x slabs] over the tile range [tile_begin, tile_end). */
-typedef struct {
-  int32_t tile_begin, tile_end;
-  int32_t n_dy_slabs;           /* 1..4 consecutive dY stash slabs (64 output features each)  */
-  int32_t n_x_slabs;            /* 1..4 consecutive X stash slabs (64 input columns each)     */
-  int32_t dy_slab, x_slab;      /* first slab inside a tile's dY / X stash                    */
-  int32_t m_real, n_real;       /* real output features / input columns covered               */
-  int64_t dst;                  /* float index of dW[m0, c0] in the flat gradient buffer      */
-  int32_t ld;                   /* row stride of W (= in_features)                            */
-  int32_t reserved;
-} NbWgradItem;
-
-#ifdef __cplusplus
-}
-#endif
+#include "../../include/nerfb200_mlp.h"

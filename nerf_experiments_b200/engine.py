@@ -1,0 +1,104 @@
+"""Training engine for the fused path: one flat fp32 parameter / gradient buffer for every
+network and the camera poses, gradients accumulated by the backward kernels straight into it,
+one NCCL all-reduce per step (rays shard across GPUs) and one fused Adam launch
+with the reference's per-group exponential learning-rate schedule
+(barf/model_interpolation.py:543-584).  It replaces, for the hot path only, what Lightning's
+automatic optimisation does for the reference; the modules remain usable under Lightning."""
+import ctypes as C
+from typing import List, Optional
+
+import torch as th
+import torch.nn as nn
+
+from ._lib import check, lib
+from .fused_mlp import FlatParams
+from .model_interpolation import le_nice_lr, log_decay_factor
+
+
+class TrainEngine:
+    def __init__(self, model, device, process_group=None, betas=(0.9, 0.999), eps: float = 1e-5):
+        """model: NerfInterpolation (or a subclass carrying `camera_extrinsics` parameters)."""
+        self.model = model
+        self.device = th.device(device)
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (th.distributed.is_available() and th.distributed.is_initialized()):
+            self.world = th.distributed.get_world_size(process_group)
+        self.betas, self.eps = betas, eps
+        self.step_count = 0
+
+        # one flat buffer: [radiance | proposal | poses]; groups follow model.param_groups
+        groups = []
+        params: List[nn.Parameter] = []
+        for g in model.param_groups:
+            ps = [p for p in g["parameters"]] if not isinstance(g["parameters"], list) else g["parameters"]
+            g["parameters"] = ps          # generators are single-use: keep the list
+            begin = sum(p.numel() for p in params)
+            params += ps
+            groups.append(dict(begin=begin, end=begin + sum(p.numel() for p in ps),
+                               lr0=g["learning_rate_start"],
+                               logf=log_decay_factor(g["learning_rate_start"], g["learning_rate_stop"],
+                                                     g["learning_rate_decay_end"]),
+                               n=g["learning_rate_decay_end"], wd=g.get("weight_decay", 0.0)))
+        self.groups = groups
+        self.flat = FlatParams(params)
+        model.to(self.device)
+        self.flat.ensure(self.device)
+        for net in (model.model_radiance, getattr(model, "model_proposal", None)):
+            if net is not None:
+                net.fused_field(flat=self.flat)
+        self.grad = th.zeros(self.flat.numel, device=self.device, dtype=th.float32)
+        self.exp_avg = th.zeros_like(self.grad)
+        self.exp_avg_sq = th.zeros_like(self.grad)
+        self.flat.grad_sink = self.grad
+        cam = getattr(model, "camera_extrinsics", None)
+        self.pose_sink = None
+        if cam is not None and hasattr(cam, "rotation"):
+            o_r, o_t = self.flat.offset_of(cam.rotation), self.flat.offset_of(cam.translation)
+            self.pose_sink = (self.grad[o_r:o_r + cam.rotation.numel()].view_as(cam.rotation),
+                              self.grad[o_t:o_t + cam.translation.numel()].view_as(cam.translation))
+        n = len(groups)
+        self._gb = (C.c_longlong * n)(*[g["begin"] for g in groups])
+        self._ge = (C.c_longlong * n)(*[g["end"] for g in groups])
+        self._gw = (C.c_float * n)(*[g["wd"] for g in groups])
+
+    # -- pieces ------------------------------------------------------------------------------
+    def learning_rates(self, step: int):
+        """lr of every group for optimiser step number `step` (1-based); matches Adam +
+        SchedulerLeNice stepping once per iteration: step k uses lr(k-1 scheduler steps)."""
+        return [le_nice_lr(g["lr0"], g["logf"], g["n"], step) for g in self.groups]
+
+    def forward_loss(self, o, d, target, img_idx=None, pixel_width=None, coarse_weight: float = 1.0):
+        m = self.model
+        cam = getattr(m, "camera_extrinsics", None)
+        if self.pose_sink is not None and img_idx is not None:
+            from . import ops
+            o, d, _, _ = ops.pose_forward(cam.rotation, cam.translation, img_idx, o, d, self.pose_sink)
+        fine, coarse = m.forward(o, d, pixel_width)
+        loss_fine = nn.functional.mse_loss(fine, target)
+        loss = loss_fine
+        if coarse is not None:
+            loss = loss + coarse_weight * nn.functional.mse_loss(coarse, target)
+        return loss, loss_fine
+
+    def optimizer_step(self):
+        self.step_count += 1
+        if self.world > 1:
+            th.distributed.all_reduce(self.grad, group=self.pg)   # NCCL over NVLink, one call per step
+        lrs = self.learning_rates(self.step_count - 1)
+        glr = (C.c_float * len(lrs))(*lrs)
+        with th.cuda.device(self.device):
+            check(lib().nerfb200_adam_step(self.flat.flat.data_ptr(), self.grad.data_ptr(),
+                                           self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                                           self.flat.numel, len(lrs), self._gb, self._ge, glr, self._gw,
+                                           self.betas[0], self.betas[1], self.eps, self.step_count,
+                                           1.0 / self.world, th.cuda.current_stream().cuda_stream), "adam_step")
+        self.flat.version += 1     # the packed bf16 weight images are stale now
+
+    def step(self, o, d, target, img_idx=None, pixel_width=None, coarse_weight: float = 1.0):
+        """One optimisation step on this rank's shard of rays; returns the (fine) loss tensor."""
+        self.grad.zero_()
+        loss, loss_fine = self.forward_loss(o, d, target, img_idx, pixel_width, coarse_weight)
+        loss.backward()
+        self.optimizer_step()
+        return loss_fine.detach()

@@ -26,8 +26,12 @@ def field_backward(ctx, g_sigma, g_rgb):
                                          want_inputs, n_rays)
     ctx.stash = ctx.masks = None
     field.flat.last_grad = flat_grad
-    grads = field.flat.grad_views(flat_grad)
-    param_grads = tuple(g if need else None for g, need in zip(grads, ctx.needs_input_grad[9:]))
+    if field.flat.grad_sink is not None:
+        param_grads = tuple(None for _ in ctx.needs_input_grad[9:])     # engine mode
+    else:
+        offs = [field.flat.offset_of(p) for p in field.own_params]
+        param_grads = tuple(flat_grad[o:o + p.numel()].view(p.shape) if need else None
+                            for p, o, need in zip(field.own_params, offs, ctx.needs_input_grad[9:]))
     return (None, None, None, None,
             d_a if ctx.needs_input_grad[4] else None,
             d_b if ctx.needs_input_grad[5] else None,

@@ -57,7 +57,7 @@ def field_samples(model, pos, dir, pixel_width=None, t_start=None, t_end=None):
     pw = _prep(pixel_width, n, 1, dev)
     t0 = _prep(t_start, n, 1, dev)
     t1 = _prep(t_end, n, 1, dev)
-    return _FieldFunction.apply(model, "samples", 1, 0, pos, dir, t0, t1, pw, *model.fused_field().flat.params)
+    return _FieldFunction.apply(model, "samples", 1, 0, pos, dir, t0, t1, pw, *model.fused_field().own_params)
 
 
 def field_rays(model, ray_o, ray_d, t_start, t_end, pixel_width, integration_strategy: str):
@@ -68,5 +68,5 @@ def field_rays(model, ray_o, ray_d, t_start, t_end, pixel_width, integration_str
     pw = None if pixel_width is None else _prep(pixel_width, B, 1, dev)
     sigma, rgb = _FieldFunction.apply(model, "rays", S, t_mode, ray_o.contiguous().float(),
                                       ray_d.contiguous().float(), t_start.contiguous(),
-                                      t_end.contiguous(), pw, *model.fused_field().flat.params)
+                                      t_end.contiguous(), pw, *model.fused_field().own_params)
     return sigma.view(B, S), rgb.view(B, S, 3)

@@ -33,6 +33,10 @@ class FlatParams:
         self.flat: Optional[th.Tensor] = None
         self.flat_grad: Optional[th.Tensor] = None
         self.version = 0   # bumped by whoever writes `flat` outside torch's version counters
+        # engine mode: when set (a flat fp32 tensor of `numel` floats), the backward kernels
+        # accumulate parameter gradients straight into it and autograd sees no parameter grads
+        self.grad_sink: Optional[th.Tensor] = None
+        self.last_grad: Optional[th.Tensor] = None
 
     def ensure(self, device) -> th.Tensor:
         ok = (self.flat is not None and self.flat.device == device and
@@ -68,9 +72,12 @@ class FlatParams:
 class FusedField:
     """Compiled tile programs + device buffers of one network (one per NerfModel instance)."""
 
-    def __init__(self, layers_fn, flat: FlatParams, pe_pos, pe_dir, sigma_bias: float = 0.0):
+    def __init__(self, layers_fn, flat: FlatParams, pe_pos, pe_dir, sigma_bias: float = 0.0,
+                 own_params=None):
         self.layers_fn = layers_fn        # callable(FlatParams) -> List[LayerSpec]
         self.flat = flat
+        # parameters of THIS network (the flat buffer may also hold other networks / the poses)
+        self.own_params = list(own_params) if own_params is not None else list(flat.params)
         self.pe_pos = pe_pos
         self.pe_dir = pe_dir
         self.sigma_bias = sigma_bias
@@ -168,7 +175,10 @@ class FusedField:
         cb = self.bwd[bool(want_input_grads)]
         n_tiles = (n + _lib.NB_TILE_ROWS - 1) // _lib.NB_TILE_ROWS
         dy_stash = th.empty(n_tiles * cb.dy_slabs_per_tile * _lib.NB_SLAB_BYTES, device=dev, dtype=th.uint8)
-        flat_grad = th.zeros(self.flat.numel, device=dev, dtype=th.float32)
+        if self.flat.grad_sink is not None:
+            flat_grad = self.flat.grad_sink
+        else:
+            flat_grad = th.zeros(self.flat.numel, device=dev, dtype=th.float32)
         d_a = d_b = None
         samples_mode = bool(inputs.pos)
         if want_input_grads:

@@ -108,7 +108,8 @@ class NerfModel(NerfBaseModel):
                                          self.delayed_direction, self.delayed_density,
                                          self.position_encoder.output_dim, self.direction_encoder.output_dim)
 
-            self._field = FusedField(layers_fn, self._flat, self.position_encoder, self.direction_encoder)
+            self._field = FusedField(layers_fn, self._flat, self.position_encoder, self.direction_encoder,
+                                     own_params=list(self.parameters()))
         return self._field
 
     def forward(self, pos: th.Tensor, dir: th.Tensor, pixel_width: th.Tensor = None,

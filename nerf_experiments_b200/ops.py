@@ -185,7 +185,8 @@ class _Pose(th.autograd.Function):
     are returned detached, as nothing in the reference differentiates through them."""
 
     @staticmethod
-    def forward(ctx, rotation, translation, img_idx, o, d):
+    def forward(ctx, rotation, translation, img_idx, o, d, grad_sink=None):
+        ctx.grad_sink = grad_sink
         B = o.shape[0]
         rotation = _f32(rotation, "rotation")
         translation = _f32(translation, "translation")
@@ -210,15 +211,22 @@ class _Pose(th.autograd.Function):
         B = d.shape[0]
         g_o = th.zeros_like(d) if g_o is None else g_o.contiguous()
         g_d = th.zeros_like(d) if g_d is None else g_d.contiguous()
-        d_rot = th.zeros_like(rotation)
-        d_tr = th.zeros_like(rotation)
+        sink = getattr(ctx, "grad_sink", None)
+        if sink is not None:      # engine mode: accumulate straight into the flat gradient buffer
+            d_rot, d_tr = sink
+        else:
+            d_rot = th.zeros_like(rotation)
+            d_tr = th.zeros_like(rotation)
         with th.cuda.device(d.device):
             check(lib().nerfb200_pose_bwd(_ptr(rotation), _ptr(idx), _ptr(d), _ptr(g_o), _ptr(g_d), B,
                                           rotation.shape[0], _ptr(d_rot), _ptr(d_tr), _stream()),
                   "pose_bwd")
         g_in_d = th.matmul(R.transpose(1, 2), g_d.unsqueeze(-1)).squeeze(-1) if ctx.needs_input_grad[4] else None
-        return d_rot, d_tr, None, (g_o if ctx.needs_input_grad[3] else None), g_in_d
+        if sink is not None:
+            d_rot = d_tr = None
+        return d_rot, d_tr, None, (g_o if ctx.needs_input_grad[3] else None), g_in_d, None
 
 
-def pose_forward(rotation, translation, img_idx, o, d):
-    return _Pose.apply(rotation, translation, img_idx, o, d)
+def pose_forward(rotation, translation, img_idx, o, d, grad_sink=None):
+    """grad_sink: optional (d_rotation, d_translation) views the backward accumulates into."""
+    return _Pose.apply(rotation, translation, img_idx, o, d, grad_sink)
