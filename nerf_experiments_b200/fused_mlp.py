@@ -84,6 +84,9 @@ class FusedField:
         self.compiled: Optional[CompiledMlp] = None
         self.device = None
         self._packed_sig = None
+        # optional per-kernel timing (bench.py): name -> list of (start, end) CUDA events
+        # recorded on the launching stream; None = off
+        self.timers = None
 
     # -- compilation / packing ------------------------------------------------------------
     def prepare(self, device):
@@ -128,6 +131,22 @@ class FusedField:
             self._packed_sig = sig
         return self.compiled
 
+    def _timed(self, name, fn):
+        if self.timers is None:
+            return fn()
+        e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        self.timers.setdefault(name, []).append((e0, e1))
+
+    def macs_per_sample(self):
+        """Algorithmic (unpadded) multiply-accumulates per sample: forward, data-gradient (with /
+        without the encoding-gradient blocks) and weight-gradient passes."""
+        fwd = sum(L.lin.out_f * L.lin.in_f for L in self.compiled.layers)
+        enc = sum(L.lin.out_f * s.width for L in self.compiled.layers for s in L.sources if s.kind != "act")
+        return {"fwd": fwd, "bwd_inputs": fwd, "bwd": fwd - enc, "wgrad": fwd}
+
     def pe_cfgs(self):
         cp = self.pe_pos.describe()
         cd = self.pe_dir.describe()
@@ -151,11 +170,10 @@ class FusedField:
             masks = th.empty(max(n_tiles * cm.mask_words_per_tile * _lib.NB_TILE_ROWS, 1), device=dev, dtype=th.int32)
         cp, cd = self.pe_cfgs()
         with th.cuda.device(dev):
-            check(lib().nerfb200_mlp_fwd(C.byref(cm.program), _ptr(self.wpack), _ptr(self.bias),
-                                         C.byref(inputs), C.byref(cp), C.byref(cd),
-                                         _ptr(self.pe_pos.alpha_tensor()), _ptr(self.pe_dir.alpha_tensor()),
-                                         float(self.sigma_bias), _ptr(sigma), _ptr(rgb), _ptr(stash),
-                                         _ptr(masks), th.cuda.current_stream().cuda_stream), "mlp_fwd")
+            self._timed("mlp_fwd_train" if training else "mlp_fwd", lambda: check(lib().nerfb200_mlp_fwd(
+                C.byref(cm.program), _ptr(self.wpack), _ptr(self.bias), C.byref(inputs), C.byref(cp), C.byref(cd),
+                _ptr(self.pe_pos.alpha_tensor()), _ptr(self.pe_dir.alpha_tensor()), float(self.sigma_bias),
+                _ptr(sigma), _ptr(rgb), _ptr(stash), _ptr(masks), th.cuda.current_stream().cuda_stream), "mlp_fwd"))
         return sigma, rgb, stash, masks
 
 
@@ -191,7 +209,7 @@ class FusedField:
         cp, cd = self.pe_cfgs()
         stream = th.cuda.current_stream().cuda_stream
         with th.cuda.device(dev):
-            check(lib().nerfb200_mlp_bwd(
+            self._timed("mlp_bwd_inputs" if want_input_grads else "mlp_bwd", lambda: check(lib().nerfb200_mlp_bwd(
                 C.byref(cb.program), _ptr(self.wpack), C.byref(inputs), C.byref(cp), C.byref(cd),
                 _ptr(self.pe_pos.alpha_tensor()), _ptr(self.pe_dir.alpha_tensor()), _ptr(sigma), _ptr(rgb),
                 _ptr(g_sigma), _ptr(g_rgb), _ptr(masks), cm.mask_words_per_tile, _ptr(dy_stash),
@@ -199,11 +217,11 @@ class FusedField:
                 cb.dir_grad_cols if want_input_grads else 0,
                 None if samples_mode else _ptr(d_a), None if samples_mode else _ptr(d_b),
                 _ptr(d_a) if samples_mode else None, _ptr(d_b) if samples_mode else None,
-                cb.head_bias_off, cm.bias_floats, _ptr(self.bias_map_dev), _ptr(flat_grad), stream), "mlp_bwd")
+                cb.head_bias_off, cm.bias_floats, _ptr(self.bias_map_dev), _ptr(flat_grad), stream), "mlp_bwd"))
             items_dev, n_items = self._items(n_tiles)
-            check(lib().nerfb200_mlp_wgrad(_ptr(items_dev), n_items, _ptr(stash), cm.stash_slabs_per_tile,
-                                           _ptr(dy_stash), cb.dy_slabs_per_tile, _ptr(flat_grad), stream),
-                  "mlp_wgrad")
+            self._timed("mlp_wgrad", lambda: check(lib().nerfb200_mlp_wgrad(
+                _ptr(items_dev), n_items, _ptr(stash), cm.stash_slabs_per_tile, _ptr(dy_stash),
+                cb.dy_slabs_per_tile, _ptr(flat_grad), stream), "mlp_wgrad"))
         return flat_grad, d_a, d_b
 
 
