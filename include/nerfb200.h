@@ -179,7 +179,7 @@ int nerfb200_mlp_fwd(const void* program_host, const void* wpack, const float* b
                      const NbMlpInputs* in_host, const NbPeCfg* pe_pos_host,
                      const NbPeCfg* pe_dir_host, const float* alpha_pos,
                      const float* alpha_dir, float sigma_bias, float* out_sigma, float* out_rgb,
-                     void* stash, uint32_t* masks, void* stream);
+                     void* stash, uint32_t* masks, int n_bias_floats, void* stream);
 int nerfb200_mlp_bwd(const void* program_host, const void* wpack_t,
                      const NbMlpInputs* in_host, const NbPeCfg* pe_pos_host,
                      const NbPeCfg* pe_dir_host, const float* alpha_pos,

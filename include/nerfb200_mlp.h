@@ -20,14 +20,14 @@ extern "C" {
 #endif
 
 enum {
-  NB_MAX_OPS = 40,
-  NB_MAX_CHUNKS = 6,
+  NB_MAX_OPS = 32,
+  NB_MAX_CHUNKS = 12,
   NB_MAX_BLOCKS = 3,
   NB_TILE_ROWS = 128,
   NB_SLAB_BYTES = 128 * 128,          /* 128 rows x 64 bf16 */
   NB_N_SLABS = 6,                     /* 0..3 activations, 4 and 5 auxiliary (PE / extra) */
-  NB_RING_STAGE_BYTES = 272 * 128,    /* largest weight image: 272 rows x 64 bf16 */
-  NB_RING_STAGES = 3
+  NB_RING_STAGE_BYTES = 256 * 128,    /* largest weight image: 256 rows x 64 bf16 */
+  NB_MAX_RING_STAGES = 4
 };
 
 /* forward epilogues */
@@ -63,6 +63,9 @@ typedef struct {
   int8_t out_chunks;                 /* 64-wide slabs the epilogue writes (act slabs 0..)       */
   int8_t a_src[NB_MAX_CHUNKS];       /* slab id of every K chunk                                */
   int8_t k16[NB_MAX_CHUNKS];         /* 16-wide MMA K steps in every chunk (1..4)               */
+  int8_t blk_mask[NB_MAX_CHUNKS];    /* bit b set: this chunk's image feeds N-block b           */
+  int8_t n_sub[NB_MAX_CHUNKS];       /* the chunk spans n_sub consecutive A slabs (a_src, +1..): */
+                                     /* n_sub images of w_rows rows each, back to back          */
   int16_t w_rows[NB_MAX_CHUNKS];     /* rows of the weight image of every chunk                 */
   int32_t w_off[NB_MAX_CHUNKS];      /* offset of the image in the packed buffer, 1024 B units  */
   NbBlock blocks[NB_MAX_BLOCKS];
@@ -76,7 +79,8 @@ typedef struct {
   int32_t n_ops;
   int32_t stash_slabs_per_tile;      /* slabs of NB_SLAB_BYTES per tile in the stash            */
   int32_t mask_words_per_tile;       /* 32-column groups per tile (x128 rows x 4 B)             */
-  int32_t reserved;
+  int16_t n_slabs;                   /* shared-memory slabs in use: 5 or 6                      */
+  int16_t n_stages;                  /* weight ring depth: 4 with 5 slabs, 3 with 6             */
   NbOp ops[NB_MAX_OPS];
 } NbProgram;
 
@@ -93,6 +97,9 @@ typedef struct {
   float pixel_width_sigma;      /* integrated PE only                                         */
   int32_t slab;                 /* destination slab id (4 or 5), -1: encoder unused           */
   int32_t stash_slab;           /* stash slab (per tile) of the encoding, -1: none            */
+  int32_t encode_before_op;     /* forward: 0 = encoded at tile start; k > 0 = encoded while  */
+                                /* op k's MMAs run (the slab is shared with an encoder whose  */
+                                /* last use is op k-1 and this encoder's first use is > k)    */
 } NbPeCfg;
 
 /* Where the samples of a launch come from.  Either per-ray data (positions are computed in the

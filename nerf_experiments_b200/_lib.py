@@ -13,13 +13,13 @@ LIB_PATH = os.path.join(_HERE, "libnerfb200.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 # ---- mirrors of csrc/mlp.h -----------------------------------------------------------------
-NB_MAX_OPS = 40
-NB_MAX_CHUNKS = 6
+NB_MAX_OPS = 32
+NB_MAX_CHUNKS = 12
 NB_MAX_BLOCKS = 3
 NB_TILE_ROWS = 128
 NB_SLAB_BYTES = 128 * 128
 NB_N_SLABS = 6
-NB_RING_STAGE_BYTES = 272 * 128
+NB_RING_STAGE_BYTES = 256 * 128
 
 EPI_RELU, EPI_LINEAR, EPI_LINEAR_SIGMA, EPI_RGB, EPI_RGB_SIGMA, EPI_RELU_SIGMA = range(6)
 BEPI_MASK, BEPI_PLAIN, BEPI_PLAIN_SIGMA, BEPI_MASK_SIGMA, BEPI_NONE = range(5)
@@ -35,6 +35,7 @@ class NbOp(C.Structure):
     _fields_ = [
         ("n_chunks", C.c_int8), ("n_blocks", C.c_int8), ("epi", C.c_int8), ("out_chunks", C.c_int8),
         ("a_src", C.c_int8 * NB_MAX_CHUNKS), ("k16", C.c_int8 * NB_MAX_CHUNKS),
+        ("blk_mask", C.c_int8 * NB_MAX_CHUNKS), ("n_sub", C.c_int8 * NB_MAX_CHUNKS),
         ("w_rows", C.c_int16 * NB_MAX_CHUNKS), ("w_off", C.c_int32 * NB_MAX_CHUNKS),
         ("blocks", NbBlock * NB_MAX_BLOCKS),
         ("bias_off", C.c_int32), ("stash_slab", C.c_int32), ("mask_word", C.c_int32),
@@ -44,14 +45,15 @@ class NbOp(C.Structure):
 
 class NbProgram(C.Structure):
     _fields_ = [("n_ops", C.c_int32), ("stash_slabs_per_tile", C.c_int32),
-                ("mask_words_per_tile", C.c_int32), ("reserved", C.c_int32),
+                ("mask_words_per_tile", C.c_int32), ("n_slabs", C.c_int16), ("n_stages", C.c_int16),
                 ("ops", NbOp * NB_MAX_OPS)]
 
 
 class NbPeCfg(C.Structure):
     _fields_ = [("kind", C.c_int32), ("levels", C.c_int32), ("include_identity", C.c_int32),
                 ("use_mask", C.c_int32), ("distribute_variance", C.c_int32), ("scale", C.c_float),
-                ("pixel_width_sigma", C.c_float), ("slab", C.c_int32), ("stash_slab", C.c_int32)]
+                ("pixel_width_sigma", C.c_float), ("slab", C.c_int32), ("stash_slab", C.c_int32),
+                ("encode_before_op", C.c_int32)]
 
 
 class NbMlpInputs(C.Structure):
@@ -120,7 +122,7 @@ def _declare(L):
     L.nerfb200_so3_to_SO3.argtypes = [vp, i32, vp, vp]
     L.nerfb200_mlp_pack.argtypes = [vp, vp, i32, vp, vp, i32, vp, vp]
     L.nerfb200_mlp_fwd.argtypes = [vp, vp, vp, C.POINTER(NbMlpInputs), C.POINTER(NbPeCfg),
-                                   C.POINTER(NbPeCfg), vp, vp, f32, vp, vp, vp, vp, vp]
+                                   C.POINTER(NbPeCfg), vp, vp, f32, vp, vp, vp, vp, i32, vp]
     L.nerfb200_mlp_bwd.argtypes = [vp, vp, C.POINTER(NbMlpInputs), C.POINTER(NbPeCfg), C.POINTER(NbPeCfg),
                                    vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, i32, i32, vp, vp, vp, vp,
                                    i32, i32, vp, vp, vp]

@@ -1,5 +1,6 @@
 // Error reporting, device queries and the launch counter of libnerfb200.so.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -21,6 +22,13 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int sm_count() {
   static int cached = 0;
+  // NERFB200_MAX_GRID limits the persistent grids (profiling experiments only)
+  static int limit = -1;
+  if (limit < 0) {
+    const char* e = getenv("NERFB200_MAX_GRID");
+    limit = e ? atoi(e) : 0;
+  }
+  if (limit > 0) return limit;
   if (cached == 0) {
     int dev = 0, n = 0;
     if (cudaGetDevice(&dev) == cudaSuccess &&

@@ -48,22 +48,29 @@ struct MlpBwdParams {
 
 constexpr uint32_t kTmemPosCol = 256;
 constexpr uint32_t kTmemDirCol = 320;
+constexpr int kHelperWarp0 = 10;         // warps 10 and 11: bias-gradient column sums
+constexpr int kBwdThreads = 384;
 
-__global__ void __launch_bounds__(kMlpThreads, 1)
+__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
 mlp_bwd_kernel(const __grid_constant__ MlpBwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  MlpSmem sm(smem_raw);
+  MlpSmem sm(smem_raw, p.prog.n_slabs, p.prog.n_stages);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_tiles = (p.N + NB_TILE_ROWS - 1) / NB_TILE_ROWS;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NB_RING_STAGES; ++s) {
+    for (int s = 0; s < NB_MAX_RING_STAGES; ++s) {
       mbar_init(&sm.full[s], 1);
       mbar_init(&sm.empty[s], 1);
     }
     mbar_init(sm.a_ready, kRowThreads);
     mbar_init(sm.acc_full, 1);
+    mbar_init(sm.epi_done, kRowThreads);
+    mbar_init(sm.helper_done, 2);
     fence_barrier_init();
     pe_fill_mask(p.pe_pos, p.alpha_pos, sm.mask_pos);
     pe_fill_mask(p.pe_dir, p.alpha_dir, sm.mask_dir);
@@ -76,56 +83,80 @@ mlp_bwd_kernel(const __grid_constant__ MlpBwdParams p) {
   const uint32_t tmem_base = *sm.tmem_ptr;
 
   if (warp == kProducerWarp) {
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int oi = 0; oi < p.prog.n_ops; ++oi) {
-          const NbOp& op = p.prog.ops[oi];
-          for (int c = 0; c < op.n_chunks; ++c) {
-            mbar_wait(&sm.empty[stage], phase ^ 1u);
-            const uint32_t bytes = (uint32_t)op.w_rows[c] * 128u;
-            mbar_arrive_expect_tx(&sm.full[stage], bytes);
-            bulk_g2s(sm.ring(stage), p.wpack + (size_t)op.w_off[c] * 1024u, bytes, &sm.full[stage]);
-            if (++stage == NB_RING_STAGES) { stage = 0; phase ^= 1u; }
-          }
-        }
-      }
-    }
+    if (lane == 0) weight_producer_loop(p.prog, p.wpack, sm, n_tiles);
   } else if (warp == kMmaWarp) {
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0, a_phase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int oi = 0; oi < p.prog.n_ops; ++oi) {
-          const NbOp& op = p.prog.ops[oi];
-          mbar_wait(sm.a_ready, a_phase);
-          a_phase ^= 1u;
-          tcgen05_fence_after();
-          for (int c = 0; c < op.n_chunks; ++c) {
-            mbar_wait(&sm.full[stage], phase);
-            tcgen05_fence_after();
-            const uint32_t a_addr = smem_u32(sm.slab(op.a_src[c]));
-            const uint32_t b_addr = smem_u32(sm.ring(stage));
-            for (int k = 0; k < op.k16[c]; ++k) {
-              const uint64_t adesc = umma_desc_kmajor(a_addr, 0, k);
-              for (int b = 0; b < op.n_blocks; ++b) {
-                const NbBlock& blk = op.blocks[b];
-                const uint64_t bdesc = umma_desc_kmajor(b_addr, blk.row0, k);
-                const uint32_t acc = (blk.accum_in || c > 0 || k > 0) ? 1u : 0u;
-                umma(tmem_base + (uint32_t)blk.tmem_col, adesc, bdesc,
-                     umma_idesc(NB_TILE_ROWS, blk.n, false, false), acc);
-              }
+    mma_issuer_loop(p.prog, sm, tmem_base, n_tiles);
+  } else if (warp >= kHelperWarp0) {
+    // ---------------- bias gradients: column sums of every dY tile, off the critical path ---
+    // Helper warp h owns slabs 2h and 2h+1. Lane = (slab sl, row half rh, physical chunk pc) sums
+    // its 16-byte chunk position over 64 rows; the swizzle (logical chunk = pc ^ (row & 7)) is
+    // undone with xor-shuffles, so every column ends with exactly one owner lane: no atomics.
+    const int h = warp - kHelperWarp0;
+    const int sl = lane >> 4, rh = (lane >> 3) & 1, pc = lane & 7;
+    const int s_idx = 2 * h + sl;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int oi = 0; oi < p.prog.n_ops; ++oi) {
+        const NbOp& op = p.prog.ops[oi];
+        if (op.epi == NB_BEPI_NONE) continue;
+        mbar_wait(sm.epi_done, ph);
+        ph ^= 1u;
+        if (op.bias_off >= 0 && 2 * h < op.out_chunks) {
+          float acc[8][8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[q][e] = 0.f;
+          const bool live = s_idx < op.out_chunks;
+          const uint8_t* base = sm.slab(live ? s_idx : 0) + (uint32_t)(rh * 64) * 128u + (uint32_t)pc * 16u;
+#pragma unroll 1
+          for (int r8 = 0; r8 < 8; ++r8) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {   // row & 7 == q
+              const uint4 v = *reinterpret_cast<const uint4*>(base + (uint32_t)(r8 * 8 + q) * 128u);
+              acc[q][0] += bf16_lo(v.x); acc[q][1] += bf16_hi(v.x);
+              acc[q][2] += bf16_lo(v.y); acc[q][3] += bf16_hi(v.y);
+              acc[q][4] += bf16_lo(v.z); acc[q][5] += bf16_hi(v.z);
+              acc[q][6] += bf16_lo(v.w); acc[q][7] += bf16_hi(v.w);
             }
-            umma_commit(&sm.empty[stage]);
-            if (++stage == NB_RING_STAGES) { stage = 0; phase ^= 1u; }
           }
-          umma_commit(sm.acc_full);
+          // lane (.., pc) holds in acc[q] the partial sums of logical chunk pc ^ q: lane c gathers
+          // acc[q] from lane c ^ q
+          float tot[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) tot[e] = acc[0][e];
+#pragma unroll
+          for (int q = 1; q < 8; ++q)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) tot[e] += __shfl_xor_sync(0xffffffffu, acc[q][e], q);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) tot[e] += __shfl_xor_sync(0xffffffffu, tot[e], 8);   // other row half
+          if (live && rh == 0) {
+            float* dst = sm.floats + op.bias_off + s_idx * 64 + pc * 8;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) dst[e] += tot[e];
+          }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sm.helper_done);
       }
     }
   } else {
-    const int row = threadIdx.x;
-    const uint32_t tmem_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
-    uint32_t acc_phase = 0;
+    const int row = threadIdx.x & (kHalfThreads - 1);
+    const int half = threadIdx.x >> 7;
+    const bool leader = (row == 0);
+    const int bar_id = 1 + half;
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    uint32_t acc_phase = 0, helper_phase = 0;
+    bool helper_pending = false;   // a helper pass may still be reading the act slabs
+    StashQueue sq;
+    auto wait_helper = [&]() {
+      if (helper_pending) {
+        mbar_wait(sm.helper_done, helper_phase);
+        helper_phase ^= 1u;
+        helper_pending = false;
+      }
+    };
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long n_raw = (long long)tile * NB_TILE_ROWS + row;
       const bool valid = n_raw < p.N;
@@ -133,16 +164,17 @@ mlp_bwd_kernel(const __grid_constant__ MlpBwdParams p) {
       uint8_t* tile_stash = p.dy_stash + (size_t)tile * p.prog.stash_slabs_per_tile * NB_SLAB_BYTES;
       const uint32_t* tile_masks = p.masks + (size_t)tile * p.fwd_mask_words_per_tile * NB_TILE_ROWS + row;
 
-      // earlier stash copies must be done reading the slabs before they are rewritten
-      if (threadIdx.x == 0) bulk_wait_read<0>();
-      named_bar_sync(1, kRowThreads);
+      // earlier stash copies / helper passes must be done reading the slabs before the rewrite
+      if (leader) sq.wait_all();
+      named_bar_sync(3, kRowThreads);
+      wait_helper();
 
-      // ---- head: gradients w.r.t. the pre-activations of the output layer ----
+      // ---- head: gradients w.r.t. the pre-activations of the output layer (half 0) ----
       const float sg = p.sigma[n];
       float d_sigma_pre = 0.f;
       if (valid && p.g_sigma != nullptr)
         d_sigma_pre = p.g_sigma[n] * (sg > 8.f ? 1.f : (1.f - __expf(-sg)));
-      {
+      if (half == 0) {
         float d4[4] = {0.f, 0.f, 0.f, 0.f};
         if (valid && p.g_rgb != nullptr) {
 #pragma unroll
@@ -158,65 +190,78 @@ mlp_bwd_kernel(const __grid_constant__ MlpBwdParams p) {
           if (lane == c) atomicAdd(&sm.floats[p.head_bias_off + c], t);
         }
         uint8_t* slab = sm.slab(0);
-        // columns 0..15 (two 16-byte pieces) of the row; only k16 = 1 is consumed
+        // columns 0..15 hold the head gradient (only k16 = 1 is consumed by the MMA); the rest of
+        // the row is cleared because wgrad consumes the stashed slab as a full 64-column operand
         *reinterpret_cast<uint4*>(slab + (uint32_t)row * 128u + ((uint32_t)(0 ^ (row & 7)) << 4)) =
             make_uint4(pack_bf16(d4[0], d4[1]), pack_bf16(d4[2], d4[3]), 0u, 0u);
-        *reinterpret_cast<uint4*>(slab + (uint32_t)row * 128u + ((uint32_t)(1 ^ (row & 7)) << 4)) =
-            make_uint4(0u, 0u, 0u, 0u);
-        // the stash slab of the head is consumed as a full 64-column slab by wgrad: clear the rest
 #pragma unroll
-        for (int q = 2; q < 8; ++q)
+        for (int q = 1; q < 8; ++q)
           *reinterpret_cast<uint4*>(slab + (uint32_t)row * 128u + ((uint32_t)(q ^ (row & 7)) << 4)) =
               make_uint4(0u, 0u, 0u, 0u);
       }
       fence_proxy_async();
       mbar_arrive(sm.a_ready);
-      named_bar_sync(1, kRowThreads);
-      if (threadIdx.x == 0) {
-        bulk_s2g(tile_stash, sm.slab(0), NB_SLAB_BYTES);   // head dY = stash slab 0
-        bulk_commit();
+      if (half == 0) {
+        named_bar_sync(bar_id, kHalfThreads);
+        if (leader) {
+          sq.begin_batch();
+          sq.push(tile_stash, sm.slab(0), NB_SLAB_BYTES);   // head dY = stash slab 0
+        }
       }
 
       for (int oi = 0; oi < p.prog.n_ops; ++oi) {
         const NbOp& op = p.prog.ops[oi];
         const bool last = (oi == p.prog.n_ops - 1);
+        const bool stores = (op.epi != NB_BEPI_NONE);
+        const bool masked = (op.epi == NB_BEPI_MASK || op.epi == NB_BEPI_MASK_SIGMA);
+        const bool with_sigma = (op.epi == NB_BEPI_PLAIN_SIGMA || op.epi == NB_BEPI_MASK_SIGMA);
+        const int c_mid = (op.out_chunks + 1) >> 1;
+        const int c_begin = half == 0 ? 0 : c_mid;
+        const int c_end = half == 0 ? c_mid : op.out_chunks;
+        // ReLU sign bits of the producing layer: fetched before the accumulator is waited for
+        uint32_t mbits[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int g = 2 * c_begin + j;
+          mbits[j] = (masked && g < 2 * c_end) ? __ldg(tile_masks + (size_t)(op.mask_word + g) * NB_TILE_ROWS)
+                                               : 0xffffffffu;
+        }
         mbar_wait(sm.acc_full, acc_phase);
         acc_phase ^= 1u;
         tcgen05_fence_after();
-        if (op.epi != NB_BEPI_NONE) {
-          if (threadIdx.x == 0) bulk_wait_read<0>();
-          named_bar_sync(1, kRowThreads);
-          const bool masked = (op.epi == NB_BEPI_MASK || op.epi == NB_BEPI_MASK_SIGMA);
-          const int groups = op.out_chunks * 2;
-          for (int g = 0; g < groups; ++g) {
-            uint32_t v[32];
-            tmem_ld32(tmem_lane + (uint32_t)(g * 32), v);
-            uint32_t bits = 0xffffffffu;
-            if (masked) bits = tile_masks[(size_t)(op.mask_word + g) * NB_TILE_ROWS];
-            tmem_ld_wait();
-            uint32_t packed[16];
-            float f[32];
+        NB_TRACE(oi * 4 + 2, threadIdx.x == 0 && tile == (int)(blockIdx.x + gridDim.x));
+        if (stores) {
+          wait_helper();
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              f[i] = ((bits >> i) & 1u) ? __uint_as_float(v[i]) : 0.f;
-              f[i + 1] = ((bits >> (i + 1)) & 1u) ? __uint_as_float(v[i + 1]) : 0.f;
-              packed[i >> 1] = pack_bf16(f[i], f[i + 1]);
-            }
-            // bias gradient of the producing layer: column sums over the tile rows
-            if (op.bias_off >= 0) {
-              const float cs = warp_colsum32(f, lane);
-              atomicAdd(&sm.floats[op.bias_off + g * 32 + lane], cs);
-            }
-            uint8_t* slab = sm.slab(g >> 1);
-            const int chunk0 = (g & 1) * 4;
+          for (int j = 0; j < 4; ++j) {
+            const int g = 2 * c_begin + j;
+            if (g < 2 * c_end) {
+              uint32_t v[32];
+              tmem_ld32(tmem_lane + (uint32_t)(g * 32), v);
+              if ((g & 1) == 0) {
+                if (leader) sq.wait_slab((g >> 1) - c_begin);
+                named_bar_sync(bar_id, kHalfThreads);
+              }
+              const uint32_t bits = mbits[j];
+              tmem_ld_wait();
+              uint32_t packed[16];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint32_t off = (uint32_t)row * 128u + ((uint32_t)((chunk0 + q) ^ (row & 7)) << 4);
-              *reinterpret_cast<uint4*>(slab + off) =
-                  make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+              for (int i = 0; i < 32; i += 2) {
+                const float a = ((bits >> i) & 1u) ? __uint_as_float(v[i]) : 0.f;
+                const float b = ((bits >> (i + 1)) & 1u) ? __uint_as_float(v[i + 1]) : 0.f;
+                packed[i >> 1] = pack_bf16(a, b);
+              }
+              uint8_t* slab = sm.slab(g >> 1);
+              const int chunk0 = (g & 1) * 4;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint32_t off = (uint32_t)row * 128u + ((uint32_t)((chunk0 + q) ^ (row & 7)) << 4);
+                *reinterpret_cast<uint4*>(slab + off) =
+                    make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+              }
             }
           }
-          if (op.epi == NB_BEPI_PLAIN_SIGMA || op.epi == NB_BEPI_MASK_SIGMA) {
+          if (with_sigma && half == 1) {
             // d(sigma_pre) becomes column 0 of the aux slab (an extra 16-wide K step)
             if (op.bias_off >= 0) {
               const float t = warp_sum(d_sigma_pre);
@@ -225,38 +270,44 @@ mlp_bwd_kernel(const __grid_constant__ MlpBwdParams p) {
             uint8_t* slab = sm.slab(4);
             *reinterpret_cast<uint4*>(slab + (uint32_t)row * 128u + ((uint32_t)(0 ^ (row & 7)) << 4)) =
                 make_uint4(pack_bf16(d_sigma_pre, 0.f), 0u, 0u, 0u);
-            *reinterpret_cast<uint4*>(slab + (uint32_t)row * 128u + ((uint32_t)(1 ^ (row & 7)) << 4)) =
-                make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-            for (int q = 2; q < 8; ++q)
+            for (int q = 1; q < 8; ++q)
               *reinterpret_cast<uint4*>(slab + (uint32_t)row * 128u + ((uint32_t)(q ^ (row & 7)) << 4)) =
                   make_uint4(0u, 0u, 0u, 0u);
           }
         }
         tcgen05_fence_before();
+        NB_TRACE(oi * 4 + 3, threadIdx.x == 0 && tile == (int)(blockIdx.x + gridDim.x));
+        if (stores) {
+          mbar_arrive(sm.epi_done);     // release: the helper warps may read the slabs
+          helper_pending = true;
+        }
         if (!last) {
           fence_proxy_async();
           mbar_arrive(sm.a_ready);
         }
-        if (op.epi != NB_BEPI_NONE && op.stash_slab >= 0) {
+        if (stores && op.stash_slab >= 0) {
           if (last) fence_proxy_async();
-          named_bar_sync(1, kRowThreads);
-          if (threadIdx.x == 0) {
-            bulk_s2g(tile_stash + (size_t)op.stash_slab * NB_SLAB_BYTES, sm.slab(0),
-                     (uint32_t)op.out_chunks * NB_SLAB_BYTES);
-            if (op.epi == NB_BEPI_PLAIN_SIGMA || op.epi == NB_BEPI_MASK_SIGMA)
-              bulk_s2g(tile_stash + (size_t)(op.stash_slab + op.out_chunks) * NB_SLAB_BYTES, sm.slab(4),
-                       NB_SLAB_BYTES);
-            bulk_commit();
+          named_bar_sync(bar_id, kHalfThreads);
+          if (leader) {
+            sq.begin_batch();
+            for (int c = c_begin; c < c_end; ++c)
+              sq.push(tile_stash + (size_t)(op.stash_slab + c) * NB_SLAB_BYTES, sm.slab(c), NB_SLAB_BYTES);
+            if (with_sigma && half == 1)
+              sq.push(tile_stash + (size_t)(op.stash_slab + op.out_chunks) * NB_SLAB_BYTES, sm.slab(4), NB_SLAB_BYTES);
           }
         }
       }
 
       // ---- gradients w.r.t. the encodings -> positions / directions -> rays ----
       if (p.want_input_grads) {
-        // all MMAs of the tile are complete (acc_full of the last op); the slabs are free
-        if (threadIdx.x == 0) bulk_wait_read<0>();
-        named_bar_sync(1, kRowThreads);
+        // all MMAs of the tile are complete (acc_full of the last op); the slabs are free once the
+        // stash copies (both halves') and the helper pass have drained
+        if (leader) sq.wait_all();
+        named_bar_sync(3, kRowThreads);
+        wait_helper();
+      }
+      if (p.want_input_grads && half == 0) {
         float* scratch = reinterpret_cast<float*>(sm.slab(0));   // [128 cols][128 rows] fp32
         auto stage_block = [&](uint32_t tmem_col, int cols, int first) {
           for (int g = 0; g < cols; g += 32) {
@@ -328,9 +379,9 @@ mlp_bwd_kernel(const __grid_constant__ MlpBwdParams p) {
             }
           }
         }
-        named_bar_sync(1, kRowThreads);   // scratch reads done before the next tile's head write
       }
     }
+    wait_helper();
     if (threadIdx.x == 0) bulk_wait_all<0>();
   }
 
@@ -348,6 +399,11 @@ mlp_bwd_kernel(const __grid_constant__ MlpBwdParams p) {
 }  // namespace nerfb200
 
 using namespace nerfb200;
+
+extern "C" int nerfb200_debug_trace_bwd(long long* trace_dev) {
+  NB_CHECK_CUDA(cudaMemcpyToSymbol(g_trace, &trace_dev, sizeof(trace_dev)));
+  return NERFB200_OK;
+}
 
 extern "C" int nerfb200_mlp_bwd(const void* program_host, const void* wpack_t,
                                 const NbMlpInputs* in_host, const NbPeCfg* pe_pos_host,
@@ -409,12 +465,12 @@ extern "C" int nerfb200_mlp_bwd(const void* program_host, const void* wpack_t,
   static bool configured = false;
   if (!configured) {
     NB_CHECK_CUDA(cudaFuncSetAttribute(mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)MlpSmem::kBytes));
+                                       (int)MlpSmem::bytes(5, 4)));  // the larger of the two layouts
     configured = true;
   }
   const int n_tiles = ceil_div(p.N, NB_TILE_ROWS);
   const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
-  mlp_bwd_kernel<<<grid, kMlpThreads, MlpSmem::kBytes, (cudaStream_t)stream>>>(p);
+  mlp_bwd_kernel<<<grid, kBwdThreads, MlpSmem::bytes(prog->n_slabs, prog->n_stages), (cudaStream_t)stream>>>(p);
   count_launch();
   NB_CHECK_LAUNCH();
   return NERFB200_OK;

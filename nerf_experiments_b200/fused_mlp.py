@@ -150,8 +150,9 @@ class FusedField:
     def pe_cfgs(self):
         cp = self.pe_pos.describe()
         cd = self.pe_dir.describe()
-        cp.slab, cp.stash_slab = SLAB_PE_POS, 0
-        cd.slab, cd.stash_slab = SLAB_PE_DIR, 1
+        cp.slab, cp.stash_slab, cp.encode_before_op = SLAB_PE_POS, 0, 0
+        cd.slab, cd.stash_slab = self.compiled.dir_slab, 1
+        cd.encode_before_op = self.compiled.dir_encode_before_op
         return cp, cd
 
     # -- launches -------------------------------------------------------------------------
@@ -173,7 +174,8 @@ class FusedField:
             self._timed("mlp_fwd_train" if training else "mlp_fwd", lambda: check(lib().nerfb200_mlp_fwd(
                 C.byref(cm.program), _ptr(self.wpack), _ptr(self.bias), C.byref(inputs), C.byref(cp), C.byref(cd),
                 _ptr(self.pe_pos.alpha_tensor()), _ptr(self.pe_dir.alpha_tensor()), float(self.sigma_bias),
-                _ptr(sigma), _ptr(rgb), _ptr(stash), _ptr(masks), th.cuda.current_stream().cuda_stream), "mlp_fwd"))
+                _ptr(sigma), _ptr(rgb), _ptr(stash), _ptr(masks), cm.bias_floats,
+                th.cuda.current_stream().cuda_stream), "mlp_fwd"))
         return sigma, rgb, stash, masks
 
 

@@ -57,6 +57,8 @@ class CompiledMlp:
     op_inputs: List[List[Tuple[int, int]]] = field(default_factory=list)
     stash_slabs_per_tile: int = 0
     mask_words_per_tile: int = 0
+    dir_slab: int = SLAB_PE_DIR
+    dir_encode_before_op: int = 0
 
 
 def nerf_model_layers(lins: dict, n_hidden: int, hidden_dim: int, n_segments: int,
@@ -99,6 +101,14 @@ def compile_forward(layers: List[LayerSpec]) -> CompiledMlp:
         raise RuntimeError(f"network too deep for one tile program ({len(layers)} > {NB_MAX_OPS} layers)")
     prog = NbProgram()
     prog.n_ops = len(layers)
+    # The direction encoding can take over slab 4 once the position encoding is dead (delayed
+    # direction): 5 slabs leave room for a 4-stage weight ring. Otherwise 6 slabs + 3 stages.
+    pos_uses = [i for i, L in enumerate(layers) if any(s.kind == "pos" for s in L.sources)]
+    dir_uses = [i for i, L in enumerate(layers) if any(s.kind == "dir" for s in L.sources)]
+    share = bool(dir_uses) and (not pos_uses or min(dir_uses) >= max(pos_uses) + 2)
+    dir_slab = SLAB_PE_POS if (share or not dir_uses) else SLAB_PE_DIR
+    dir_before = (max(pos_uses) + 1) if share and pos_uses else 0   # encoded while that op's MMAs run
+    prog.n_slabs, prog.n_stages = (6, 3) if (dir_uses and not share) else (5, 4)
     chunks: List[NbPackChunk] = []
     biases: List[NbPackBias] = []
     w_units = 0          # 1024 B units used in the packed weight buffer
@@ -135,36 +145,67 @@ def compile_forward(layers: List[LayerSpec]) -> CompiledMlp:
             else:
                 if src.width > 64:
                     raise RuntimeError(f"{src.kind} encoding wider than 64 columns is not supported")
-                slab = SLAB_PE_POS if src.kind == "pos" else SLAB_PE_DIR
+                slab = SLAB_PE_POS if src.kind == "pos" else dir_slab
                 inputs.append((slab, col, src.width, 0 if src.kind == "pos" else 1))
                 col += src.width
         if col != lin.in_f:
             raise RuntimeError(f"layer {li}: sources cover {col} columns, weight has {lin.in_f}")
-        if len(inputs) > NB_MAX_CHUNKS:
+        # the density row rides in the same image when it fits a ring stage, else in images of
+        # its own (one 16-row image per K chunk, feeding only the extra block)
+        split_extra = extra and rows_img * 128 > _lib.NB_RING_STAGE_BYTES
+        n_entries = len(inputs) * (2 if split_extra else 1)
+        for ci in range(NB_MAX_CHUNKS):
+            op.n_sub[ci] = 1
+        if n_entries > NB_MAX_CHUNKS:
             raise RuntimeError(f"layer {li}: too many K chunks")
-        op.n_chunks = len(inputs)
+        op.n_chunks = n_entries
         rec = []
         for ci, (slab, c0, w, st) in enumerate(inputs):
             op.a_src[ci] = slab
             op.k16[ci] = _ceil(w, 16)
-            op.w_rows[ci] = rows_img
+            op.w_rows[ci] = n_main if split_extra else rows_img
             op.w_off[ci] = w_units
+            op.blk_mask[ci] = 1 if (split_extra or not extra) else 3
             # main rows
             chunks.append(NbPackChunk(base=lin.w_off + c0, row_stride=lin.in_f, col_stride=1,
                                       n_rows=min(L.out_main, lin.out_f) if L.act != "rgb" else lin.out_f,
                                       n_cols=w, rows_padded=n_main, dst_off=w_units))
-            if extra:
+            if extra and not split_extra:
                 chunks.append(NbPackChunk(base=lin.w_off + L.out_main * lin.in_f + c0, row_stride=lin.in_f,
                                           col_stride=1, n_rows=1, n_cols=w, rows_padded=16,
                                           dst_off=w_units + n_main // 8))
-            w_units += rows_img // 8
+            w_units += op.w_rows[ci] // 8
             rec.append((st, _ceil(w, 16)))
+        if split_extra:
+            # runs of consecutive full-width act slabs share one image (one ring slot)
+            ci = len(inputs)
+            cj = 0
+            while cj < len(inputs):
+                slab, c0, w, st = inputs[cj]
+                run = 1
+                while (cj + run < len(inputs) and inputs[cj + run][0] == slab + run and w == 64
+                       and inputs[cj + run][2] == 64):
+                    run += 1
+                op.a_src[ci] = slab
+                op.k16[ci] = _ceil(w, 16)
+                op.w_rows[ci] = 16
+                op.w_off[ci] = w_units
+                op.blk_mask[ci] = 2
+                op.n_sub[ci] = run
+                for r in range(run):
+                    _, c0r, wr, _ = inputs[cj + r]
+                    chunks.append(NbPackChunk(base=lin.w_off + L.out_main * lin.in_f + c0r, row_stride=lin.in_f,
+                                              col_stride=1, n_rows=1, n_cols=wr, rows_padded=16, dst_off=w_units))
+                    w_units += 2
+                ci += 1
+                cj += run
+            op.n_chunks = ci
         op_inputs.append(rec)
         # blocks
         op.n_blocks = 2 if extra else 1
         op.blocks[0] = NbBlock(0, n_main, 0, 0)
         if extra:
-            op.blocks[1] = NbBlock(TMEM_EXTRA_COL, 16, n_main, 0)
+            op.blocks[1] = NbBlock(TMEM_EXTRA_COL, 16, 0 if split_extra else n_main, 0)
         # bias
         op.bias_off = bias_floats
         biases.append(NbPackBias(base=lin.b_off, n=(L.out_main if L.act != "rgb" else lin.out_f),
@@ -199,7 +240,7 @@ def compile_forward(layers: List[LayerSpec]) -> CompiledMlp:
     return CompiledMlp(program=prog, pack_chunks=chunks, pack_biases=biases,
                        wpack_bytes=w_units * 1024, bias_floats=bias_floats, layers=layers,
                        op_inputs=op_inputs, stash_slabs_per_tile=stash,
-                       mask_words_per_tile=mask_words)
+                       mask_words_per_tile=mask_words, dir_slab=dir_slab, dir_encode_before_op=dir_before)
 
 
 def to_device_array(items, ctype, device):
@@ -297,6 +338,8 @@ def compile_backward(cm: CompiledMlp, want_input_grads: bool) -> CompiledBackwar
                 op.k16[ci] = k16
                 op.w_rows[ci] = n_block
                 op.w_off[ci] = w_units
+                op.blk_mask[ci] = 1
+                op.n_sub[ci] = 1
                 chunks.append(NbPackChunk(base=lin.w_off + krow0 * lin.in_f + col_first, row_stride=1,
                                           col_stride=lin.in_f, n_rows=width, n_cols=kcols,
                                           rows_padded=n_block, dst_off=w_units))
@@ -341,6 +384,7 @@ def compile_backward(cm: CompiledMlp, want_input_grads: bool) -> CompiledBackwar
         prog.ops[i] = op
     prog.stash_slabs_per_tile = dy_slabs_per_tile
     prog.mask_words_per_tile = cm.mask_words_per_tile
+    prog.n_slabs, prog.n_stages = 5, 4
 
     bias_map = [-1] * cm.bias_floats
     for pb in cm.pack_biases:
