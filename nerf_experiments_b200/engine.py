@@ -13,6 +13,7 @@ import torch.nn as nn
 from ._lib import check, lib
 from .fused_mlp import FlatParams
 from .model_interpolation import le_nice_lr, log_decay_factor
+from .parallel import allreduce_sum_, global_mean_scale
 
 
 class TrainEngine:
@@ -64,8 +65,9 @@ class TrainEngine:
 
     # -- pieces ------------------------------------------------------------------------------
     def learning_rates(self, step: int):
-        """lr of every group for optimiser step number `step` (1-based); matches Adam +
-        SchedulerLeNice stepping once per iteration: step k uses lr(k-1 scheduler steps)."""
+        """lr of every group for optimiser step number `step` (1-based).  torch's LRScheduler
+        performs one scheduler step at construction, so the reference's k-th optimiser step
+        runs with the closed form evaluated at _step_count = k."""
         return [le_nice_lr(g["lr0"], g["logf"], g["n"], step) for g in self.groups]
 
     def forward_loss(self, o, d, target, img_idx=None, pixel_width=None, coarse_weight: float = 1.0):
@@ -84,15 +86,15 @@ class TrainEngine:
     def optimizer_step(self):
         self.step_count += 1
         if self.world > 1:
-            th.distributed.all_reduce(self.grad, group=self.pg)   # NCCL over NVLink, one call per step
-        lrs = self.learning_rates(self.step_count - 1)
+            allreduce_sum_(self.grad, self.pg)   # NCCL over NVLink, one call per step
+        lrs = self.learning_rates(self.step_count)
         glr = (C.c_float * len(lrs))(*lrs)
         with th.cuda.device(self.device):
             check(lib().nerfb200_adam_step(self.flat.flat.data_ptr(), self.grad.data_ptr(),
                                            self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
                                            self.flat.numel, len(lrs), self._gb, self._ge, glr, self._gw,
                                            self.betas[0], self.betas[1], self.eps, self.step_count,
-                                           1.0 / self.world, th.cuda.current_stream().cuda_stream), "adam_step")
+                                           global_mean_scale(self.world), th.cuda.current_stream().cuda_stream), "adam_step")
         self.flat.version += 1     # the packed bf16 weight images are stale now
 
     def step(self, o, d, target, img_idx=None, pixel_width=None, coarse_weight: float = 1.0):

@@ -1,0 +1,28 @@
+"""Multi-GPU plumbing of the hot path: rays are independent, so every rank takes
+a contiguous shard of each batch; parameters are replicated and their gradients summed with ONE
+all-reduce per step over the flat fp32 gradient buffer (NCCL on GPUs, gloo in the CPU tests)."""
+from typing import Tuple
+
+import torch as th
+import torch.distributed as dist
+
+
+def shard_range(n_rays: int, rank: int, world: int) -> Tuple[int, int]:
+    """[begin, end) of the rays rank `rank` of `world` takes out of n_rays (contiguous blocks,
+    the remainder spread over the first ranks)."""
+    base, rem = divmod(n_rays, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def allreduce_sum_(flat_grad: th.Tensor, group=None) -> th.Tensor:
+    """In-place sum of the flat gradient buffer over the ranks (one collective per step)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+    return flat_grad
+
+
+def global_mean_scale(world: int) -> float:
+    """Every rank's loss is a mean over its own shard; with equal shards the gradient of the
+    global mean is the rank sum divided by the world size (barf/model_interpolation.py:508)."""
+    return 1.0 / world
