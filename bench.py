@@ -211,7 +211,7 @@ def run_ours(args):
                                 "frac": round(v["tflops"] / peak, 4)} for k, v in kernels.items()},
                 "mlp_share_of_step": round(sum(v["ms"] for v in kernels.values()) / (ms_total / K), 4)}
 
-    cpu = cpu_baseline_sample(steps=2, rays=256)
+    cpu = cpu_baseline_sample(steps=2, rays=256) if world == 1 else None   # N=1 only (tier rule)
     rays_total = world * RAYS_PER_GPU * K
     out = {
         "metric": METRIC, "value": rays_total / (ms_total * 1e-3), "unit": "rays/s", "n_gpus": world,
