@@ -165,12 +165,12 @@ int nerfb200_pe_bwd(const NbPeCfg* cfg_host, const float* alpha, const float* po
  *                     16 KiB) and the ReLU sign bits (masks: n_tiles * mask_words_per_tile * 128
  *                     uint32).
  * nerfb200_mlp_bwd    data gradients: walks the layers in reverse, writes every dY as bf16 slabs
- *                     (dy_stash: n_tiles * program.stash_slabs_per_tile * 16 KiB), accumulates
- *                     the bias gradients into d_params (+=) and, if pos_grad_cols/dir_grad_cols
- *                     are non-zero, the gradients w.r.t. ray origins / directions (+=, caller
- *                     zeroes) or per-sample positions / directions.
- * nerfb200_mlp_wgrad  weight gradients dW += dY^T X over the work items (NbWgradItem, DEVICE
- *                     array) into d_params.
+ *                     (dy_stash: n_tiles * program.stash_slabs_per_tile * 16 KiB) and, if
+ *                     pos_grad_cols/dir_grad_cols are non-zero, accumulates (+=, caller zeroes)
+ *                     the gradients w.r.t. ray origins / directions or per-sample positions /
+ *                     directions.
+ * nerfb200_mlp_wgrad  weight gradients dW += dY^T X and bias gradients db += column sums of dY
+ *                     over the work items (NbWgradItem, DEVICE array) into d_params.
  */
 int nerfb200_mlp_pack(const float* params, const NbPackChunk* chunks_dev, int n_chunks,
                       void* wpack, const NbPackBias* biases_dev, int n_biases,
@@ -187,8 +187,7 @@ int nerfb200_mlp_bwd(const void* program_host, const void* wpack_t,
                      const float* g_sigma, const float* g_rgb, const uint32_t* masks,
                      int fwd_mask_words_per_tile, void* dy_stash, int head_sigma_col3,
                      int pos_grad_cols, int dir_grad_cols, float* d_ray_o, float* d_ray_d,
-                     float* d_pos, float* d_dir, int head_bias_off, int n_bias_floats,
-                     const int32_t* bias_map, float* d_params, void* stream);
+                     float* d_pos, float* d_dir, void* stream);
 int nerfb200_mlp_wgrad(const NbWgradItem* items_dev, int n_items, const void* x_stash,
                        int x_slabs_per_tile, const void* dy_stash, int dy_slabs_per_tile,
                        float* d_params, void* stream);

@@ -46,11 +46,20 @@ enum {
   NB_BEPI_PLAIN = 1,      /* dY_prev = acc -> act slabs (+dY stash)                            */
   NB_BEPI_PLAIN_SIGMA = 2,/* as PLAIN and d(sigma_pre) -> aux slab 4 col 0                     */
   NB_BEPI_MASK_SIGMA = 3, /* as MASK and d(sigma_pre) -> aux slab 4 col 0                      */
-  NB_BEPI_NONE = 4        /* nothing to store (only persistent PE-gradient blocks written)     */
+  NB_BEPI_NONE = 4,       /* nothing to store                                                  */
+  NB_BEPI_PEGRAD_POS = 5, /* acc = d(position encoding) in the canonical column order (below): */
+  NB_BEPI_PEGRAD_DIR = 6  /* pushed through the encoder into d(position) / d(direction)        */
 };
 
+/* Canonical column order of an encoding-gradient accumulator (NB_BEPI_PEGRAD_*): the gradient
+ * w.r.t. cos(coordinate c, level j) sits in column 2*(NB_PE_CANON_LEVELS*c + j), the one w.r.t.
+ * sin(c, j) in the next column, the identity columns in 60..62 — whatever the encoder's real
+ * level count, so that the kernel can keep the 64 columns in registers. */
+enum { NB_PE_CANON_LEVELS = 10, NB_PE_CANON_COLS = 64, NB_PE_CANON_IDENTITY = 60 };
+
 typedef struct {
-  int16_t tmem_col;   /* first accumulator column                                             */
+  int16_t tmem_col;   /* first accumulator column inside the op's 256-column buffer; values   */
+                      /* >= 256 address column (tmem_col - 256) of the OTHER buffer            */
   int16_t n;          /* MMA N (multiple of 16, <= 256)                                        */
   int16_t row0;       /* first row of the weight image used as B (multiple of 8)               */
   int16_t accum_in;   /* 1: accumulate onto what an earlier op left in these columns           */
@@ -120,14 +129,18 @@ typedef struct {
   int32_t reserved;
 } NbMlpInputs;
 
-/* A packed weight image: image(r,c) = params[base + r*row_stride + c*col_stride] for
- * r < n_rows, c < n_cols, zero elsewhere; rows_padded rows of 64 bf16, swizzled slab layout. */
+/* A packed weight image: value(r,c) = params[base + r*row_stride + c*col_stride] for
+ * r < n_rows, c < n_cols, zero elsewhere, is written for r < rows_padded to image row
+ * dst_row0 + r*dst_row_step (rows of 64 bf16, swizzled slab layout). Rows no descriptor
+ * writes keep the zeros the packed buffer was initialised with. */
 typedef struct {
   int64_t base;
   int32_t row_stride, col_stride;
   int32_t n_rows, n_cols;
   int32_t rows_padded;
   int32_t dst_off;              /* 1024 B units into the packed buffer                        */
+  int32_t dst_row0;             /* first image row written                                    */
+  int32_t dst_row_step;         /* image-row step (>= 1)                                      */
 } NbPackChunk;
 
 /* A packed bias segment: dst[dst_off + i] = params[base + i] for i < n, 0 for n <= i < n_padded */
@@ -148,7 +161,9 @@ typedef struct {
   int32_t m_real, n_real;       /* real output features / input columns covered               */
   int64_t dst;                  /* float index of dW[m0, c0] in the flat gradient buffer      */
   int32_t ld;                   /* row stride of W (= in_features)                            */
-  int32_t reserved;
+  int32_t bias_dst;             /* float index of the bias gradient of output feature m0 (the */
+                                /* column sums of the dY slabs, += over the tile range), -1:  */
+                                /* another item of the same dY slabs carries it               */
 } NbWgradItem;
 
 #ifdef __cplusplus

@@ -22,7 +22,8 @@ NB_N_SLABS = 6
 NB_RING_STAGE_BYTES = 256 * 128
 
 EPI_RELU, EPI_LINEAR, EPI_LINEAR_SIGMA, EPI_RGB, EPI_RGB_SIGMA, EPI_RELU_SIGMA = range(6)
-BEPI_MASK, BEPI_PLAIN, BEPI_PLAIN_SIGMA, BEPI_MASK_SIGMA, BEPI_NONE = range(5)
+BEPI_MASK, BEPI_PLAIN, BEPI_PLAIN_SIGMA, BEPI_MASK_SIGMA, BEPI_NONE, BEPI_PEGRAD_POS, BEPI_PEGRAD_DIR = range(7)
+PE_CANON_LEVELS, PE_CANON_COLS, PE_CANON_IDENTITY = 10, 64, 60
 PE_IDENTITY, PE_FOURIER, PE_INTEGRATED = range(3)
 COMPOSITE_BARF, COMPOSITE_NERFACC = 0, 1
 
@@ -66,7 +67,12 @@ class NbMlpInputs(C.Structure):
 class NbPackChunk(C.Structure):
     _fields_ = [("base", C.c_int64), ("row_stride", C.c_int32), ("col_stride", C.c_int32),
                 ("n_rows", C.c_int32), ("n_cols", C.c_int32), ("rows_padded", C.c_int32),
-                ("dst_off", C.c_int32)]
+                ("dst_off", C.c_int32), ("dst_row0", C.c_int32), ("dst_row_step", C.c_int32)]
+
+    def __init__(self, *args, **kw):
+        kw.setdefault("dst_row0", 0)
+        kw.setdefault("dst_row_step", 1)
+        super().__init__(*args, **kw)
 
 
 class NbPackBias(C.Structure):
@@ -78,7 +84,7 @@ class NbWgradItem(C.Structure):
     _fields_ = [("tile_begin", C.c_int32), ("tile_end", C.c_int32), ("n_dy_slabs", C.c_int32),
                 ("n_x_slabs", C.c_int32), ("dy_slab", C.c_int32), ("x_slab", C.c_int32),
                 ("m_real", C.c_int32), ("n_real", C.c_int32), ("dst", C.c_int64), ("ld", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("bias_dst", C.c_int32)]
 
 
 _lib = None
@@ -124,8 +130,7 @@ def _declare(L):
     L.nerfb200_mlp_fwd.argtypes = [vp, vp, vp, C.POINTER(NbMlpInputs), C.POINTER(NbPeCfg),
                                    C.POINTER(NbPeCfg), vp, vp, f32, vp, vp, vp, vp, i32, vp]
     L.nerfb200_mlp_bwd.argtypes = [vp, vp, C.POINTER(NbMlpInputs), C.POINTER(NbPeCfg), C.POINTER(NbPeCfg),
-                                   vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, i32, i32, vp, vp, vp, vp,
-                                   i32, i32, vp, vp, vp]
+                                   vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, i32, i32, vp, vp, vp, vp, vp]
     L.nerfb200_mlp_wgrad.argtypes = [vp, i32, vp, i32, vp, i32, vp, vp]
     L.nerfb200_adam_step.argtypes = [vp, vp, vp, vp, C.c_longlong, i32, vp, vp, vp, vp, f32, f32, f32,
                                      C.c_longlong, f32, vp]

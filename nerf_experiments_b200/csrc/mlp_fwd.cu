@@ -5,8 +5,11 @@
 // (reference barf/model_interpolation.py:288-312, barf/model_interpolation_architecture.py:96-141)
 // — 12 cuBLAS GEMMs + ~40 elementwise launches in the reference — by one persistent launch.
 //
-// CTA = 6 warps: warps 0-3 own one tile row each (TMEM lane = row), warp 4 issues MMAs,
-// warp 5 streams weight images through a 3-stage ring.
+// CTA = 11 warps: warps 0-7 row threads (TMEM lane = tile row, two column halves), warp 8
+// issues MMAs, warp 9 streams weight images through the ring, warp 10 copies activation slabs
+// to the HBM stash (training). Consecutive layers alternate between two TMEM accumulator
+// buffers and hand activations over slab by slab, so the tensor pipe works on layer l+1 while
+// the row threads are still in the epilogue of layer l (see mlp_kernels.cuh).
 #include "common.cuh"
 #include "mlp.h"
 #include "mlp_kernels.cuh"
@@ -18,34 +21,85 @@ namespace {
 
 using namespace tc;
 
-// packs relu(a+b) (or a+b) pairs to bf16x2 and collects the ReLU sign bits
-__device__ __forceinline__ uint32_t act_pack(float a0, float a1, bool relu, uint32_t& bits, int i) {
-  if (relu) {
-    // bit = 1 <=> value > 0 (sign bit clear and non-zero)
-    bits |= ((a0 > 0.f) ? 1u : 0u) << i;
-    bits |= ((a1 > 0.f) ? 1u : 0u) << (i + 1);
-    a0 = fmaxf(a0, 0.f);
-    a1 = fmaxf(a1, 0.f);
+// where a forward production goes in the per-tile stash (-1: nowhere)
+struct FwdStashDst {
+  const MlpFwdParams& p;
+  const TileSchedule& sc;
+  __device__ __forceinline__ int operator()(int ph, int s) const {
+    if (ph < 0) {
+      if (p.pe_pos.slab == s) return p.pe_pos.stash_slab;
+      return p.pe_dir.stash_slab;
+    }
+    if (ph == sc.reencode_op && ((sc.reencode_mask >> s) & 1u)) return p.pe_dir.stash_slab;
+    const NbOp& op = p.prog.ops[ph];
+    return op.stash_slab >= 0 ? op.stash_slab + s : -1;
   }
-  return pack_bf16(a0, a1);
+};
+
+// One 16-column group of an activation epilogue: bias, ReLU + sign bits, bf16 pack.
+// Returns the sign half-word: bit i set <=> pre-activation i is not negative.
+template <bool kRelu>
+__device__ __forceinline__ uint32_t act_math16(const uint32_t (&v)[16], const float* bias16,
+                                               uint32_t (&packed)[8]) {
+  // two independent sign chains (one long funnel-shift chain is latency bound): chain c collects
+  // elements 8c..8c+7, the first element ends up in the highest of its 8 bits
+  uint32_t neg[2] = {0u, 0u};
+  const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < 16; i += 4) {
+    const float4 bq = *reinterpret_cast<const float4*>(bias16 + i);
+    const float a0 = __uint_as_float(v[i]) + bq.x, a1 = __uint_as_float(v[i + 1]) + bq.y;
+    const float a2 = __uint_as_float(v[i + 2]) + bq.z, a3 = __uint_as_float(v[i + 3]) + bq.w;
+    if (kRelu) {
+      uint32_t& n = neg[i >> 3];
+      n = __funnelshift_l(__float_as_uint(a0), n, 1);
+      n = __funnelshift_l(__float_as_uint(a1), n, 1);
+      n = __funnelshift_l(__float_as_uint(a2), n, 1);
+      n = __funnelshift_l(__float_as_uint(a3), n, 1);
+    }
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(a0, a1), p1 = __floats2bfloat162_rn(a2, a3);
+    if (kRelu) {   // on the packed pairs: half the instructions of an fp32 max
+      p0 = __hmax2(p0, zero);
+      p1 = __hmax2(p1, zero);
+    }
+    packed[i >> 1] = *reinterpret_cast<uint32_t*>(&p0);
+    packed[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&p1);
+  }
+  if (!kRelu) return 0xffffu;
+  // element i sits at bit 15 - i of the merged half-word; reverse to bit i
+  const uint32_t merged = ((neg[0] & 0xffu) << 8) | (neg[1] & 0xffu);
+  return (~(__brev(merged) >> 16)) & 0xffffu;
+}
+// the two swizzled 16-byte stores of (row, column quarter cq)
+__device__ __forceinline__ void store_packed16(const uint32_t (&packed)[8], uint8_t* slab, int row, int cq) {
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const uint32_t off = (uint32_t)row * 128u + ((uint32_t)((2 * cq + q) ^ (row & 7)) << 4);
+    *reinterpret_cast<uint4*>(slab + off) =
+        make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+  }
 }
 
-__global__ void __launch_bounds__(kMlpThreads, 1)
+__global__ void __launch_bounds__(kFwdThreads, 1)
 mlp_fwd_kernel(const __grid_constant__ MlpFwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   MlpSmem sm(smem_raw, p.prog.n_slabs, p.prog.n_stages);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_tiles = (p.N + NB_TILE_ROWS - 1) / NB_TILE_ROWS;
+  const bool training = (p.stash != nullptr);
+
+  TileSchedule sched;
+  sched.is_bwd = 0;
+  sched.start_mask = 0u;
+  if (p.pe_pos.slab >= 0) sched.start_mask |= 1u << p.pe_pos.slab;
+  const bool dir_at_start = (p.pe_dir.slab >= 0 && p.pe_dir.encode_before_op == 0);
+  if (dir_at_start) sched.start_mask |= 1u << p.pe_dir.slab;
+  sched.reencode_op = (p.pe_dir.slab >= 0 && p.pe_dir.encode_before_op > 0) ? p.pe_dir.encode_before_op : -1;
+  sched.reencode_mask = sched.reencode_op >= 0 ? (1u << p.pe_dir.slab) : 0u;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NB_MAX_RING_STAGES; ++s) {
-      mbar_init(&sm.full[s], 1);
-      mbar_init(&sm.empty[s], 1);
-    }
-    mbar_init(sm.a_ready, kRowThreads);
-    mbar_init(sm.acc_full, 1);
-    fence_barrier_init();
+    sm.init_barriers();
     pe_fill_mask(p.pe_pos, p.alpha_pos, sm.mask_pos);
     pe_fill_mask(p.pe_dir, p.alpha_dir, sm.mask_dir);
   }
@@ -59,133 +113,134 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdParams p) {
   if (warp == kProducerWarp) {
     if (lane == 0) weight_producer_loop(p.prog, p.wpack, sm, n_tiles);
   } else if (warp == kMmaWarp) {
-    mma_issuer_loop(p.prog, sm, tmem_base, n_tiles);
+    mma_issuer_loop(p.prog, sched, sm, tmem_base, n_tiles);
+  } else if (warp == kStashWarp) {
+    if (training && lane == 0)
+      stash_loop(p.prog, sched, sm, n_tiles, p.stash, p.prog.stash_slabs_per_tile, FwdStashDst{p, sched});
   } else {
-    // ---------------- row threads: PE prologue + epilogues ----------------
-    const int row = threadIdx.x & (kHalfThreads - 1);   // tile row
-    const int half = threadIdx.x >> 7;                  // which half of the columns
-    const bool leader = (row == 0);                     // owns this half's stash copies
-    const int bar_id = 1 + half;                        // named barrier of this half
+    // ---------------- row threads: encodings + epilogues ----------------
+    const int row = threadIdx.x & kTileRowMask;         // tile row
+    const int cq = threadIdx.x >> 7;                    // which 16-column quarter of every slab
     const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    uint32_t acc_phase = 0;
-    const bool training = (p.stash != nullptr);
-    StashQueue sq;
+    const FwdStashDst dst_of{p, sched};
+    DrainBits drain;       // stash copies that must finish before a slab is rewritten
+    NB_TRACE_INIT();
+    uint32_t g_op = 0;
+    auto stashed = [&](int ph, uint32_t mask) {
+      uint32_t out = 0u;
+      for (uint32_t m = mask; m; m &= m - 1u) {
+        const int s = __ffs(m) - 1;
+        if (dst_of(ph, s) >= 0) out |= 1u << s;
+      }
+      return out;
+    };
+    uint16_t* const masks16 = reinterpret_cast<uint16_t*>(p.masks);
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long n_raw = (long long)tile * NB_TILE_ROWS + row;
       const bool valid = n_raw < p.N;
       const long long n = valid ? n_raw : (long long)p.N - 1;
-      uint8_t* tile_stash = training ? p.stash + (size_t)tile * p.prog.stash_slabs_per_tile * NB_SLAB_BYTES : nullptr;
 
-      // the previous tile's stash copies must have finished reading the encoding slabs
-      if (training) {
-        if (leader) sq.wait_all();
-        named_bar_sync(bar_id, kHalfThreads);
-      }
-      // ---- positions and positional encodings: half 0 -> position slab; half 1 -> direction slab
-      //      when it has a slab of its own (otherwise it shares slab 4 and is written later)
+      // ---- positions and positional encodings: quarter 0 -> position slab; quarter 1 ->
+      //      direction slab when it has one of its own (otherwise it shares slab 4 and is written
+      //      later). All MMAs of the previous tile have completed (its last accumulator was read).
       {
-        PeSample ps;
-        load_sample(p.in, n, ps);
-        if (half == 0) {
+        if (training) drain.acquire_mask(sm.slab_drained, sched.start_mask, lane);
+        if (cq == 0) {
+          PeSample ps;
+          load_sample(p.in, n, ps);
           encode_to_slab(p.pe_pos, sm.mask_pos, ps, sm, row);
-        } else if (p.pe_dir.encode_before_op == 0) {
-          PeSample pd = ps;  // the direction encoder sees the direction as its "position"
-          pd.x[0] = ps.dir[0]; pd.x[1] = ps.dir[1]; pd.x[2] = ps.dir[2];
+        } else if (cq == 1 && dir_at_start) {
+          PeSample pd;       // the direction encoder sees the direction as its "position"
+          load_sample(p.in, n, pd);
+          pd.x[0] = pd.dir[0]; pd.x[1] = pd.dir[1]; pd.x[2] = pd.dir[2];
           encode_to_slab(p.pe_dir, sm.mask_dir, pd, sm, row);
         }
-      }
-      fence_proxy_async();
-      mbar_arrive(sm.a_ready);
-      if (training) {
-        named_bar_sync(bar_id, kHalfThreads);
-        if (leader) {
-          const NbPeCfg& cfg = half == 0 ? p.pe_pos : p.pe_dir;
-          if (cfg.slab >= 0 && cfg.stash_slab >= 0 && (half == 0 || cfg.encode_before_op == 0)) {
-            bulk_s2g(tile_stash + (size_t)cfg.stash_slab * NB_SLAB_BYTES, sm.slab(cfg.slab), NB_SLAB_BYTES);
-            bulk_commit();
-          }
-          sq.begin_batch();   // that copy reads slab 4/5 only: act slabs may be rewritten at once
-        }
+        signal_slabs(sm.slab_ready, sched.start_mask, lane);
+        if (training) drain.produced(stashed(-1, sched.start_mask));
       }
 
       for (int oi = 0; oi < p.prog.n_ops; ++oi) {
         const NbOp& op = p.prog.ops[oi];
-        const bool last = (oi == p.prog.n_ops - 1);
         const float* bias = sm.floats + op.bias_off;
-        const bool stores_act = (op.epi == NB_EPI_RELU || op.epi == NB_EPI_LINEAR ||
-                                 op.epi == NB_EPI_LINEAR_SIGMA || op.epi == NB_EPI_RELU_SIGMA);
-        // slabs of this half: [c_begin, c_end)
-        const int c_mid = (op.out_chunks + 1) >> 1;
-        const int c_begin = half == 0 ? 0 : c_mid;
-        const int c_end = half == 0 ? c_mid : op.out_chunks;
-        if (p.pe_dir.slab >= 0 && p.pe_dir.encode_before_op == oi && oi > 0 && half == 0) {
-          // While this op's MMAs run: the direction encoding takes over the slab the position
-          // encoding no longer needs (its last reader was the previous op).
-          if (training) {
-            if (leader) sq.wait_all();
-            named_bar_sync(bar_id, kHalfThreads);
+        const bool stores_act = fwd_stores_act(op.epi);
+        const uint32_t buf = g_op & 1u;
+        const uint32_t acc = tmem_lane + buf * kAccCols;
+        if (oi == sched.reencode_op) {
+          // The direction encoding takes over the slab the position encoding no longer needs
+          // (its last reader was op oi-1, whose accumulator these threads have already seen).
+          if (training) drain.acquire_mask(sm.slab_drained, sched.reencode_mask, lane);
+          if (cq == 1) {
+            PeSample pd;
+            load_sample(p.in, n, pd);
+            pd.x[0] = pd.dir[0]; pd.x[1] = pd.dir[1]; pd.x[2] = pd.dir[2];
+            encode_to_slab(p.pe_dir, sm.mask_dir, pd, sm, row);
           }
-          PeSample pd;
-          load_sample(p.in, n, pd);
-          pd.x[0] = pd.dir[0]; pd.x[1] = pd.dir[1]; pd.x[2] = pd.dir[2];
-          encode_to_slab(p.pe_dir, sm.mask_dir, pd, sm, row);
-          if (training && p.pe_dir.stash_slab >= 0) {
-            fence_proxy_async();
-            named_bar_sync(bar_id, kHalfThreads);
-            if (leader) {
-              bulk_s2g(tile_stash + (size_t)p.pe_dir.stash_slab * NB_SLAB_BYTES, sm.slab(p.pe_dir.slab), NB_SLAB_BYTES);
-              bulk_commit();
-              sq.begin_batch();
-            }
-          }
+          signal_slabs(sm.slab_ready, sched.reencode_mask, lane);
+          if (training && p.pe_dir.stash_slab >= 0) drain.produced(sched.reencode_mask);
         }
-        mbar_wait(sm.acc_full, acc_phase);
-        acc_phase ^= 1u;
+        warp_mbar_wait(&sm.acc_full[buf], (g_op >> 1) & 1u, lane);
         tcgen05_fence_after();
-        NB_TRACE(oi * 4 + 2, threadIdx.x == 0 && tile == (int)(blockIdx.x + gridDim.x));
+        NB_TRACE(oi * 4 + 2, threadIdx.x == 0);
         if (stores_act) {
           const bool relu = (op.epi == NB_EPI_RELU || op.epi == NB_EPI_RELU_SIGMA);
-          uint32_t* mask_out = (training && op.mask_word >= 0)
-              ? p.masks + ((size_t)tile * p.prog.mask_words_per_tile + op.mask_word) * NB_TILE_ROWS + row
-              : nullptr;
-          for (int g = 2 * c_begin; g < 2 * c_end; ++g) {
-            uint32_t v[32];
-            tmem_ld32(tmem_lane + (uint32_t)(g * 32), v);
-            if (training && (g & 1) == 0) {
-              // slab g/2 is about to be rewritten: its stash copy must have drained
-              if (leader) sq.wait_slab((g >> 1) - c_begin);
-              named_bar_sync(bar_id, kHalfThreads);
-            }
+          const int oc = op.out_chunks;
+          if ((op.epi == NB_EPI_LINEAR_SIGMA || op.epi == NB_EPI_RELU_SIGMA) && cq == 3) {
+            // the density column sits in the first columns of the other buffer: it must be read
+            // before slab 0 is published (the next op's MMAs reuse that buffer from then on)
+            uint32_t e[16];
+            const uint32_t col = (uint32_t)op.blocks[1].tmem_col;
+            tmem_ld16(tmem_lane + (col >= kAccCols ? (buf ^ 1u) * kAccCols + (col - kAccCols) : buf * kAccCols + col), e);
             tmem_ld_wait();
-            uint32_t bits = 0;
-            uint32_t packed[16];
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 bq = *reinterpret_cast<const float4*>(bias + g * 32 + i);
-              packed[i >> 1] = act_pack(__uint_as_float(v[i]) + bq.x, __uint_as_float(v[i + 1]) + bq.y, relu, bits, i);
-              packed[(i >> 1) + 1] = act_pack(__uint_as_float(v[i + 2]) + bq.z, __uint_as_float(v[i + 3]) + bq.w, relu, bits, i + 2);
-            }
-            uint8_t* slab = sm.slab(g >> 1);
-            const int chunk0 = (g & 1) * 4;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint32_t off = (uint32_t)row * 128u + ((uint32_t)((chunk0 + q) ^ (row & 7)) << 4);
-              *reinterpret_cast<uint4*>(slab + off) =
-                  make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
-            }
-            if (mask_out != nullptr && relu) mask_out[(size_t)g * NB_TILE_ROWS] = bits;
-          }
-          if ((op.epi == NB_EPI_LINEAR_SIGMA || op.epi == NB_EPI_RELU_SIGMA) && half == 1) {
-            uint32_t v[16];
-            tmem_ld16(tmem_lane + (uint32_t)op.blocks[1].tmem_col, v);
-            tmem_ld_wait();
-            const float pre = __uint_as_float(v[0]) + bias[op.blocks[0].n];
+            const float pre = __uint_as_float(e[0]) + bias[op.blocks[0].n];
             if (valid) p.out_sigma[n] = softplus8(pre + p.sigma_bias);
           }
-        } else if (half == 0) {
+          // sign bits: one 32-bit word per (row, 32-column group), this thread owns half of it
+          uint16_t* mask_out = (training && relu && op.mask_word >= 0)
+              ? masks16 + (((size_t)tile * p.prog.mask_words_per_tile + op.mask_word + (cq >> 1)) * NB_TILE_ROWS + row) * 2 + (cq & 1)
+              : nullptr;
+          const uint32_t will_stash = (training && op.stash_slab >= 0) ? 1u : 0u;
+          // the TMEM load of slab j+1 is in flight during the math of slab j
+          uint32_t va[16], vb[16], packed[8];
+          const float* bias_q = bias + 16 * cq;
+          const uint32_t acc_q = acc + (uint32_t)(16 * cq);
+          tmem_ld16(acc_q, va);
+          auto finish = [&](int j, uint32_t bits) {
+            const bool tr = threadIdx.x == 0 && oi == 2 && j == 1;
+            NB_TRACE(385, tr);
+            // slab j is about to be rewritten: its stash copy must have drained
+            drain.acquire(sm.slab_drained, j, lane);
+            NB_TRACE(386, tr);
+            store_packed16(packed, sm.slab(j), row, cq);
+            if (mask_out != nullptr) mask_out[(size_t)(2 * j) * NB_TILE_ROWS * 2] = (uint16_t)bits;
+            NB_TRACE(387, tr);
+            fence_proxy_async();
+            NB_TRACE(388, tr);
+            __syncwarp();
+            NB_TRACE(389, tr);
+            if (lane == 0) mbar_arrive(&sm.slab_ready[j]);
+            NB_TRACE(390, tr);
+            drain.produced(will_stash << j);
+          };
+#pragma unroll
+          for (int j = 0; j < 4; j += 2) {
+            if (j < oc) {
+              tmem_ld_wait16(va);
+              if (j + 1 < oc) tmem_ld16(acc_q + (uint32_t)(64 * (j + 1)), vb);
+              finish(j, relu ? act_math16<true>(va, bias_q + 64 * j, packed) : act_math16<false>(va, bias_q + 64 * j, packed));
+            }
+            if (j + 1 < oc) {
+              NB_TRACE(383, threadIdx.x == 0 && oi == 2 && j == 0);
+              tmem_ld_wait16(vb);
+              NB_TRACE(384, threadIdx.x == 0 && oi == 2 && j == 0);
+              if (j + 2 < oc) tmem_ld16(acc_q + (uint32_t)(64 * (j + 2)), va);
+              finish(j + 1, relu ? act_math16<true>(vb, bias_q + 64 * (j + 1), packed)
+                                 : act_math16<false>(vb, bias_q + 64 * (j + 1), packed));
+            }
+          }
+        } else if (cq == 0) {
           // NB_EPI_RGB / NB_EPI_RGB_SIGMA: first 16 accumulator columns hold the outputs
           uint32_t v[16];
-          tmem_ld16(tmem_lane, v);
+          tmem_ld16(acc, v);
           tmem_ld_wait();
           if (valid) {
             p.out_rgb[n * 3 + 0] = sigmoidf(__uint_as_float(v[0]) + bias[0]);
@@ -195,24 +250,14 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdParams p) {
               p.out_sigma[n] = softplus8(__uint_as_float(v[3]) + bias[3] + p.sigma_bias);
           }
         }
+        // this accumulator buffer has been read out
         tcgen05_fence_before();
-        NB_TRACE(oi * 4 + 3, threadIdx.x == 0 && tile == (int)(blockIdx.x + gridDim.x));
-        if (!last) {
-          fence_proxy_async();
-          mbar_arrive(sm.a_ready);
-        }
-        if (training && stores_act && op.stash_slab >= 0) {
-          if (last) fence_proxy_async();
-          named_bar_sync(bar_id, kHalfThreads);
-          if (leader) {
-            sq.begin_batch();
-            for (int c = c_begin; c < c_end; ++c)
-              sq.push(tile_stash + (size_t)(op.stash_slab + c) * NB_SLAB_BYTES, sm.slab(c), NB_SLAB_BYTES);
-          }
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.tmem_free[buf]);
+        NB_TRACE(oi * 4 + 3, threadIdx.x == 0);
+        ++g_op;
       }
     }
-    if (training && leader) bulk_wait_all<0>();
   }
 
   tcgen05_fence_before();
@@ -274,7 +319,7 @@ extern "C" int nerfb200_mlp_fwd(const void* program_host, const void* wpack, con
   }
   const int n_tiles = ceil_div(p.N, NB_TILE_ROWS);
   const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
-  mlp_fwd_kernel<<<grid, kMlpThreads, MlpSmem::bytes(prog->n_slabs, prog->n_stages), (cudaStream_t)stream>>>(p);
+  mlp_fwd_kernel<<<grid, kFwdThreads, MlpSmem::bytes(prog->n_slabs, prog->n_stages), (cudaStream_t)stream>>>(p);
   count_launch();
   NB_CHECK_LAUNCH();
   return NERFB200_OK;

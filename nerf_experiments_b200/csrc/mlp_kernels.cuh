@@ -8,16 +8,24 @@
 
 namespace nerfb200 {
 
-// Warp roles. Warps 0-7 are the "row threads": thread t owns tile row (t & 127) — the TMEM lane
-// quarter of a warp is fixed by (warp & 3) — and column half (t >> 7) of every accumulator, so
-// two warps per SM sub-partition share the epilogue of each row.
-constexpr int kRowThreads = 256;
-constexpr int kHalfThreads = 128;
-constexpr int kMmaWarp = 8;
-constexpr int kProducerWarp = 9;
-constexpr int kMlpThreads = 320;
+// Warp roles. Warps 0-15 are the "row threads": thread t owns tile row (t & 127) — the TMEM lane
+// quarter of a warp is fixed by (warp & 3) — and the 16-column quarter (t >> 7) of every
+// 64-column slab of an accumulator, so a slab of the next layer's input is complete (and its
+// MMAs can start) as soon as the sixteen warps have passed it. Four row warps per scheduler
+// hide the TMEM / shared-memory / barrier latencies of one another; the epilogue is issue-bound
+// (one FADD, one funnel shift, half a convert and half a max per element). Warp 16 issues the
+// MMAs, warp 17 streams the weight images, warp 18 copies finished slabs to the HBM stash.
+constexpr int kRowWarps = 16;
+constexpr int kRowThreads = 512;
+constexpr int kTileRowMask = 127;
+constexpr int kMmaWarp = 16;
+constexpr int kProducerWarp = 17;
+constexpr int kStashWarp = 18;
+constexpr int kFwdThreads = 608;
 constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kAccCols = 256;      // two accumulator buffers: consecutive ops alternate
 constexpr uint32_t kWeightCopyBytes = 8192;
+constexpr int kMaxSlabs = 8;
 
 // Dynamic shared memory of the MLP kernels: n_slabs slabs | n_stages ring stages | control |
 // floats. (5 slabs + 4 stages or 6 slabs + 3 stages, chosen by the program.)
@@ -31,16 +39,16 @@ struct MlpSmem {
 
   uint8_t* base;
   uint8_t* ring_base;
-  uint64_t* full;      // [NB_MAX_RING_STAGES]
-  uint64_t* empty;     // [NB_MAX_RING_STAGES]
-  uint64_t* a_ready;
-  uint64_t* acc_full;
-  uint64_t* epi_done;     // backward: row threads -> bias-gradient helper warps
-  uint64_t* helper_done;  // backward: helper warps -> row threads
+  uint64_t* full;          // [NB_MAX_RING_STAGES] weight image landed
+  uint64_t* empty;         // [NB_MAX_RING_STAGES] weight image consumed
+  uint64_t* slab_ready;    // [kMaxSlabs] row warps -> MMA / stash / helper warps: slab (re)written
+  uint64_t* slab_drained;  // [kMaxSlabs] stash warp -> row warps: the stash copy has read the slab
+  uint64_t* acc_full;      // [2] MMA warp -> row warps: accumulator buffer complete
+  uint64_t* tmem_free;     // [2] row warps -> MMA warp: accumulator buffer read out
   uint32_t* tmem_ptr;
-  float* mask_pos;     // [kMaxLevels]
-  float* mask_dir;     // [kMaxLevels]
-  float* floats;       // [kMaxBiasFloats] biases (forward) / bias-gradient accumulators (backward)
+  float* mask_pos;         // [kMaxLevels]
+  float* mask_dir;         // [kMaxLevels]
+  float* floats;           // [kMaxBiasFloats] packed biases (forward)
   int n_stages;
 
   __device__ MlpSmem(uint8_t* b, int n_slabs, int n_stages_) : base(b), n_stages(n_stages_) {
@@ -48,20 +56,185 @@ struct MlpSmem {
     uint8_t* c = ring_base + (uint32_t)n_stages_ * NB_RING_STAGE_BYTES;
     full = reinterpret_cast<uint64_t*>(c);
     empty = full + NB_MAX_RING_STAGES;
-    a_ready = empty + NB_MAX_RING_STAGES;
-    acc_full = a_ready + 1;
-    epi_done = acc_full + 1;
-    helper_done = epi_done + 1;
-    tmem_ptr = reinterpret_cast<uint32_t*>(helper_done + 1);
-    mask_pos = reinterpret_cast<float*>(c + 128);
+    slab_ready = empty + NB_MAX_RING_STAGES;
+    slab_drained = slab_ready + kMaxSlabs;
+    acc_full = slab_drained + kMaxSlabs;
+    tmem_free = acc_full + 2;
+    tmem_ptr = reinterpret_cast<uint32_t*>(tmem_free + 2);
+    mask_pos = reinterpret_cast<float*>(c + 256);
     mask_dir = mask_pos + kMaxLevels;
     floats = reinterpret_cast<float*>(c + kCtrlBytes);
   }
   __device__ uint8_t* slab(int i) const { return base + (uint32_t)i * NB_SLAB_BYTES; }
   __device__ uint8_t* ring(int s) const { return ring_base + (uint32_t)s * NB_RING_STAGE_BYTES; }
+
+  // thread 0, before the CTA-wide barrier
+  __device__ void init_barriers() const {
+    for (int s = 0; s < NB_MAX_RING_STAGES; ++s) {
+      tc::mbar_init(&full[s], 1);
+      tc::mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < kMaxSlabs; ++s) {
+      tc::mbar_init(&slab_ready[s], kRowWarps);
+      tc::mbar_init(&slab_drained[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(&acc_full[b], 1);
+      tc::mbar_init(&tmem_free[b], kRowWarps);
+    }
+    tc::fence_barrier_init();
+  }
 };
 static_assert(MlpSmem::bytes(5, 4) <= 227 * 1024 && MlpSmem::bytes(6, 3) <= 227 * 1024, "shared memory budget");
 static_assert(NB_RING_STAGE_BYTES % 1024 == 0, "ring stages must keep 1024 B alignment");
+static_assert((2 * NB_MAX_RING_STAGES + 2 * kMaxSlabs + 5) * 8 + 4 <= 256, "control block layout");
+
+// ---- who writes which slab when ----------------------------------------------------------------
+// Every role of the CTA replays the same production schedule of a tile: "phase -1" is the tile
+// start (encodings / head gradient), phase oi is what the row threads write around op oi's
+// epilogue. A production of slab s = one completion of slab_ready[s] (all eight row warps arrive,
+// whether or not they wrote part of it).
+struct TileSchedule {
+  uint32_t start_mask;      // slabs written at tile start
+  int reencode_op;          // forward: phase that starts by re-encoding a shared slab (-1: none)
+  uint32_t reencode_mask;
+  int is_bwd;
+};
+
+__device__ __forceinline__ bool fwd_stores_act(int epi) {
+  return epi == NB_EPI_RELU || epi == NB_EPI_LINEAR || epi == NB_EPI_LINEAR_SIGMA || epi == NB_EPI_RELU_SIGMA;
+}
+__device__ __forceinline__ bool bwd_stores(int epi) {
+  return epi == NB_BEPI_MASK || epi == NB_BEPI_PLAIN || epi == NB_BEPI_PLAIN_SIGMA || epi == NB_BEPI_MASK_SIGMA;
+}
+__device__ __forceinline__ bool bwd_with_sigma(int epi) {
+  return epi == NB_BEPI_PLAIN_SIGMA || epi == NB_BEPI_MASK_SIGMA;
+}
+constexpr int kBwdAuxSlab = 4;   // backward: d(sigma_pre) column
+
+// slabs the epilogue of `op` writes
+__device__ __forceinline__ uint32_t op_out_mask(const NbOp& op, int is_bwd) {
+  if (!is_bwd) return fwd_stores_act(op.epi) ? ((1u << op.out_chunks) - 1u) : 0u;
+  if (!bwd_stores(op.epi)) return 0u;
+  return ((1u << op.out_chunks) - 1u) | (bwd_with_sigma(op.epi) ? (1u << kBwdAuxSlab) : 0u);
+}
+__device__ __forceinline__ uint32_t phase_mask(const TileSchedule& sc, const NbProgram& prog, int oi) {
+  return (oi == sc.reencode_op ? sc.reencode_mask : 0u) | op_out_mask(prog.ops[oi], sc.is_bwd);
+}
+
+// Consumer-side bookkeeping of slab productions: 4-bit pending count and phase parity per slab.
+// A waiter must never fall two phases behind an mbarrier, so every role consumes (acquires)
+// every production of the slabs it tracks before the next one can be made.
+struct SlabTracker {
+  uint32_t pending = 0;
+  uint32_t parity = 0;
+  __device__ __forceinline__ void produced(uint32_t mask) {
+    while (mask) {
+      const int s = __ffs(mask) - 1;
+      mask &= mask - 1u;
+      pending += 1u << (4 * s);
+    }
+  }
+  __device__ __forceinline__ void acquire(uint64_t* bars, int s) {
+    while ((pending >> (4 * s)) & 15u) {
+      tc::mbar_wait(&bars[s], (parity >> s) & 1u);
+      parity ^= 1u << s;
+      pending -= 1u << (4 * s);
+    }
+  }
+  // Warp-collective form: lane 0 polls, the warp follows through __syncwarp (32 lanes polling the
+  // same mbarrier serialise in the shared-memory pipe: ~500 cycles per wait with 8 warps).
+  __device__ __forceinline__ void acquire_warp(uint64_t* bars, int s, int lane) {
+    if ((pending >> (4 * s)) & 15u) {
+      if (lane == 0) {
+        uint32_t pd = pending, pr = parity;
+        while ((pd >> (4 * s)) & 15u) {
+          tc::mbar_wait(&bars[s], (pr >> s) & 1u);
+          pr ^= 1u << s;
+          pd -= 1u << (4 * s);
+        }
+      }
+      while ((pending >> (4 * s)) & 15u) {   // every lane replays the bookkeeping
+        parity ^= 1u << s;
+        pending -= 1u << (4 * s);
+      }
+      __syncwarp();
+    }
+  }
+  __device__ __forceinline__ void acquire_mask_warp(uint64_t* bars, uint32_t mask, int lane) {
+    while (mask) {
+      const int s = __ffs(mask) - 1;
+      mask &= mask - 1u;
+      acquire_warp(bars, s, lane);
+    }
+  }
+  __device__ __forceinline__ void acquire_all_warp(uint64_t* bars, int lane) {
+    if (pending == 0u) return;
+#pragma unroll
+    for (int s = 0; s < kMaxSlabs; ++s) acquire_warp(bars, s, lane);
+  }
+  __device__ __forceinline__ void acquire_mask(uint64_t* bars, uint32_t mask) {
+    while (mask) {
+      const int s = __ffs(mask) - 1;
+      mask &= mask - 1u;
+      acquire(bars, s);
+    }
+  }
+  __device__ __forceinline__ void acquire_all(uint64_t* bars) {
+    if (pending == 0u) return;
+#pragma unroll
+    for (int s = 0; s < kMaxSlabs; ++s) acquire(bars, s);
+  }
+};
+
+// Row-thread view of the stash copies: at most one copy per slab is ever outstanding, so one
+// pending bit and one parity bit per slab suffice (no loops in the epilogue's hot path).
+struct DrainBits {
+  uint32_t pending = 0, parity = 0;
+  __device__ __forceinline__ void produced(uint32_t mask) { pending |= mask; }
+  // warp-collective: lane 0 polls slab_drained[s] if a copy of slab s is outstanding
+  __device__ __forceinline__ void acquire(uint64_t* bars, int s, int lane) {
+    if ((pending >> s) & 1u) {
+      tc::mbar_wait(&bars[s], (parity >> s) & 1u);
+      parity ^= 1u << s;
+      pending &= ~(1u << s);
+    }
+  }
+  __device__ __forceinline__ void acquire_mask(uint64_t* bars, uint32_t mask, int lane) {
+    mask &= pending;
+    while (mask) {
+      const int s = __ffs(mask) - 1;
+      mask &= mask - 1u;
+      acquire(bars, s, lane);
+    }
+  }
+};
+
+// publish one slab: proxy fence, then one arrival per warp
+__device__ __forceinline__ void signal_slab(uint64_t* slab_ready, int s, int lane) {
+  tc::fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) tc::mbar_arrive(&slab_ready[s]);
+}
+
+// lane 0 polls, the warp follows
+__device__ __forceinline__ void warp_mbar_wait(uint64_t* bar, uint32_t parity, int lane) {
+  (void)lane;
+  tc::mbar_wait(bar, parity);   // one warp-wide TRYWAIT (+ hardware sleep): cheaper than a divergent leader poll
+}
+
+// Row warps: publish the slabs in `mask` (generic-proxy writes -> async proxy, one arrival per warp).
+__device__ __forceinline__ void signal_slabs(const uint64_t* slab_ready, uint32_t mask, int lane) {
+  tc::fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) {
+    while (mask) {
+      const int s = __ffs(mask) - 1;
+      mask &= mask - 1u;
+      tc::mbar_arrive(const_cast<uint64_t*>(&slab_ready[s]));
+    }
+  }
+}
 
 struct MlpFwdParams {
   NbProgram prog;
@@ -78,31 +251,6 @@ struct MlpFwdParams {
   uint8_t* stash;
   uint32_t* masks;
   int n_bias_floats;
-};
-
-// Thread-0 bookkeeping of the shared->global stash copies in flight. Every slab goes out as
-// its own bulk group, in slab order, so that the next epilogue can start rewriting slab j as
-// soon as the copies that read slabs <= j have drained, while the later slabs still stream out.
-struct StashQueue {
-  int last_batch = 0;
-  __device__ __forceinline__ void begin_batch() { last_batch = 0; }
-  __device__ __forceinline__ void push(void* gdst, const void* ssrc, uint32_t bytes) {
-    tc::bulk_s2g(gdst, ssrc, bytes);
-    tc::bulk_commit();
-    ++last_batch;
-  }
-  // returns once every copy reading act slab j (or an older batch) has finished reading
-  __device__ __forceinline__ void wait_slab(int j) const {
-    int allow = last_batch - 1 - j;
-    switch (allow) {
-      case 4: tc::bulk_wait_read<4>(); break;
-      case 3: tc::bulk_wait_read<3>(); break;
-      case 2: tc::bulk_wait_read<2>(); break;
-      case 1: tc::bulk_wait_read<1>(); break;
-      default: tc::bulk_wait_read<0>(); break;
-    }
-  }
-  __device__ __forceinline__ void wait_all() const { tc::bulk_wait_read<0>(); }
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -152,12 +300,16 @@ __device__ __forceinline__ void encode_to_slab(const NbPeCfg& cfg, const float* 
 }
 
 // Optional cycle trace (debug builds of the profiling scripts): when non-null, block 0 records
-// clock64() stamps of its second tile, 4 per op: [a_ready seen, MMAs issued, acc_full seen,
+// clock64() stamps of its second tile, 4 per op: [buffer free seen, MMAs issued, acc_full seen,
 // epilogue done].
 static __device__ long long* g_trace = nullptr;
-#define NB_TRACE(slot, cond)                                                   \
-  do {                                                                         \
-    if (g_trace != nullptr && blockIdx.x == 0 && (cond)) g_trace[(slot)] = clock64(); \
+// every role loads the pointer once (`NB_TRACE_INIT(tile0)`), block 0 traces its second tile
+#define NB_TRACE_INIT()                                                                         \
+  long long* const nb_trace_ptr = (blockIdx.x == 0) ? *(long long* volatile*)&g_trace : nullptr; \
+  const int nb_trace_tile = (int)(blockIdx.x + gridDim.x)
+#define NB_TRACE(slot, cond)                                                          \
+  do {                                                                                \
+    if (nb_trace_ptr != nullptr && tile == nb_trace_tile && (cond)) nb_trace_ptr[(slot)] = clock64(); \
   } while (0)
 
 // ---- warp-specialised loops shared by the forward and backward-data kernels ------------------
@@ -174,7 +326,6 @@ __device__ __forceinline__ void weight_producer_loop(const NbProgram& prog, cons
         const uint32_t bytes = (uint32_t)op.w_rows[c] * 128u * (uint32_t)op.n_sub[c];
         const uint8_t* src = wpack + (size_t)op.w_off[c] * 1024u;
         tc::mbar_wait(&sm.empty[stage], phase ^ 1u);
-        NB_TRACE(64 + oi * 8 + c, tile == (int)(blockIdx.x + gridDim.x) && oi < 4);
         tc::mbar_arrive_expect_tx(&sm.full[stage], bytes);
         // several smaller copies per image keep more requests in flight in the TMA engine
         for (uint32_t off = 0; off < bytes; off += kWeightCopyBytes) {
@@ -192,31 +343,43 @@ __device__ __forceinline__ void weight_producer_loop(const NbProgram& prog, cons
 // MMA. (Issuing from inside an `if (lane == 0)` region made every tcgen05.mma a ~300-cycle
 // R2UR + elect waterfall loop.) Only the elected lane executes tcgen05.mma / tcgen05.commit.
 // The descriptor high words are constant; per MMA only the 14-bit start-address field changes.
-__device__ __forceinline__ void mma_issuer_loop(const NbProgram& prog, const MlpSmem& sm,
-                                                uint32_t tmem_base_in, int n_tiles) {
+//
+// Pipelining: op g accumulates into TMEM buffer (g & 1), so its MMAs run while the row threads
+// still read op g-1's accumulator; each K chunk is issued as soon as the slab it reads has been
+// published (slab_ready), i.e. the MMAs of a layer trail the epilogue of the previous layer by
+// one slab instead of waiting for all of it.
+__device__ __forceinline__ void mma_issuer_loop(const NbProgram& prog, const TileSchedule& sched,
+                                                const MlpSmem& sm, uint32_t tmem_base_in, int n_tiles) {
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_in, 0);   // provably uniform
   const uint32_t desc_hi = (uint32_t)(tc::umma_desc(0u, 0u, 1024u) >> 32);
   const uint32_t slab0 = tc::smem_u32(sm.slab(0)) >> 4;
   const uint32_t ring0 = tc::smem_u32(sm.ring(0)) >> 4;
   const bool elected = tc::elect_one();
-  uint32_t stage = 0, phase = 0, a_phase = 0;
+  uint32_t stage = 0, phase = 0, g_op = 0;
+  SlabTracker trk;
+  NB_TRACE_INIT();
+  uint32_t carry = 0;   // productions of the phase before the next op
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     for (int oi = 0; oi < prog.n_ops; ++oi) {
       const NbOp& op = prog.ops[oi];
       const int n_chunks = op.n_chunks, n_blocks = op.n_blocks;
+      trk.produced(carry | (oi == 0 ? sched.start_mask : 0u));
+      carry = phase_mask(sched, prog, oi);
+      const uint32_t buf = g_op & 1u;
       uint32_t idesc[NB_MAX_BLOCKS], tcol[NB_MAX_BLOCKS], brow[NB_MAX_BLOCKS], acc_in[NB_MAX_BLOCKS];
 #pragma unroll
       for (int b = 0; b < NB_MAX_BLOCKS; ++b) {
         const NbBlock blk = op.blocks[b < n_blocks ? b : 0];
         idesc[b] = tc::umma_idesc(NB_TILE_ROWS, blk.n, false, false);
-        tcol[b] = tmem_base + (uint32_t)blk.tmem_col;
+        const uint32_t col = (uint32_t)blk.tmem_col;
+        tcol[b] = tmem_base + (col >= kAccCols ? (buf ^ 1u) * kAccCols + (col - kAccCols) : buf * kAccCols + col);
         brow[b] = (uint32_t)blk.row0 * 8u;               // row0 * 128 B >> 4
-        acc_in[b] = blk.accum_in ? 1u : 0u;
+        acc_in[b] = 0u;
       }
-      tc::mbar_wait(sm.a_ready, a_phase);
-      a_phase ^= 1u;
+      // the accumulator buffer must have been read out by the epilogue of op g-2
+      if (g_op >= 2u) tc::mbar_wait(&sm.tmem_free[buf], ((g_op >> 1) - 1u) & 1u);
       tc::tcgen05_fence_after();
-      NB_TRACE(oi * 4 + 0, elected && tile == (int)(blockIdx.x + gridDim.x));
+      NB_TRACE(oi * 4 + 0, elected);
       for (int c = 0; c < n_chunks; ++c) {
         uint32_t a_lo = slab0 + (uint32_t)op.a_src[c] * (NB_SLAB_BYTES >> 4);
         uint32_t b_lo = ring0 + stage * (NB_RING_STAGE_BYTES >> 4);
@@ -224,9 +387,11 @@ __device__ __forceinline__ void mma_issuer_loop(const NbProgram& prog, const Mlp
         const int bmask = op.blk_mask[c];
         const int n_sub = op.n_sub[c];
         const uint32_t sub_stride = (uint32_t)op.w_rows[c] * 8u;   // image rows * 128 B >> 4
+        for (int sub = 0; sub < n_sub; ++sub) trk.acquire(sm.slab_ready, op.a_src[c] + sub);
+        NB_TRACE(128 + oi * 8 + c, elected && oi < 16 && c < 8);
         tc::mbar_wait(&sm.full[stage], phase);
+        NB_TRACE(256 + oi * 8 + c, elected && oi < 16 && c < 8);
         tc::tcgen05_fence_after();
-        NB_TRACE(128 + oi * 8 + c, elected && tile == (int)(blockIdx.x + gridDim.x) && oi < 4);
         for (int sub = 0; sub < n_sub; ++sub) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -248,11 +413,58 @@ __device__ __forceinline__ void mma_issuer_loop(const NbProgram& prog, const Mlp
         if (elected) tc::umma_commit(&sm.empty[stage]);
         if (++stage == (uint32_t)sm.n_stages) { stage = 0; phase ^= 1u; }
       }
-      if (elected) tc::umma_commit(sm.acc_full);
-      NB_TRACE(oi * 4 + 1, elected && tile == (int)(blockIdx.x + gridDim.x));
+      // consume the productions this op did not read, so that no barrier runs two phases ahead
+      trk.acquire_all(sm.slab_ready);
+      if (elected) tc::umma_commit(&sm.acc_full[buf]);
+      NB_TRACE(oi * 4 + 1, elected);
       __syncwarp();
+      ++g_op;
     }
   }
+}
+
+// Stash copier (one thread): every published slab that has a place in the HBM stash goes out as
+// one cp.async.bulk; when the copies of a phase have finished reading shared memory the slabs
+// are handed back to the row warps (slab_drained). dst_of(phase, slab) -> stash slab or -1.
+template <typename DstFn>
+__device__ __forceinline__ void stash_loop(const NbProgram& prog, const TileSchedule& sched,
+                                           const MlpSmem& sm, int n_tiles, uint8_t* stash,
+                                           int slabs_per_tile, DstFn dst_of) {
+  SlabTracker trk;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    uint8_t* tile_stash = stash + (size_t)tile * slabs_per_tile * NB_SLAB_BYTES;
+    for (int ph = -1; ph < prog.n_ops; ++ph) {
+      const uint32_t mask = ph < 0 ? sched.start_mask : phase_mask(sched, prog, ph);
+      if (mask == 0u) continue;
+      const uint32_t first = (ph >= 0 && ph == sched.reencode_op) ? sched.reencode_mask : 0u;
+      int prev = -1;   // slab of the newest copy in flight
+      trk.produced(mask);
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+        uint32_t m = pass == 0 ? first : (mask & ~first);
+        while (m) {
+          const int s = __ffs(m) - 1;
+          m &= m - 1u;
+          trk.acquire(sm.slab_ready, s);
+          const int d = dst_of(ph, s);
+          if (d >= 0) {
+            tc::bulk_s2g(tile_stash + (size_t)d * NB_SLAB_BYTES, sm.slab(s), NB_SLAB_BYTES);
+            tc::bulk_commit();
+            if (prev >= 0) {               // the copy before this one has read its slab
+              tc::bulk_wait_read<1>();
+              tc::mbar_arrive(&sm.slab_drained[prev]);
+            }
+            prev = s;
+          }
+        }
+      }
+      if (prev >= 0) {
+        tc::bulk_wait_read<0>();
+        tc::mbar_arrive(&sm.slab_drained[prev]);
+      }
+    }
+  }
+  tc::bulk_wait_all<0>();
 }
 
 // Column sums over the 32 lanes of a warp: lane i holds v[0..31] (one matrix row); on return
@@ -293,7 +505,13 @@ inline int validate_program(const NbProgram& prog) {
     for (int b = 0; b < op.n_blocks; ++b) {
       const NbBlock& k = op.blocks[b];
       NB_CHECK_ARG(k.n >= 16 && k.n <= 256 && k.n % 16 == 0, "program op %d: block n=%d", i, k.n);
-      NB_CHECK_ARG(k.tmem_col >= 0 && k.tmem_col + k.n <= (int)kTmemCols, "program op %d: tmem_col=%d", i, k.tmem_col);
+      NB_CHECK_ARG(k.tmem_col >= 0 && (k.tmem_col % (int)kAccCols) + k.n <= (int)kAccCols && k.tmem_col < 2 * (int)kAccCols,
+                   "program op %d: tmem_col=%d", i, k.tmem_col);
+      // a block in the other accumulator buffer lands on columns the previous epilogue reads
+      // first: safe only if every MMA of the op is issued after slab 0 has been published
+      if (k.tmem_col >= (int)kAccCols)
+        NB_CHECK_ARG((i == 0 || op.a_src[0] == 0) && k.tmem_col - (int)kAccCols + k.n <= 32,
+                     "program op %d: side block needs slab 0 as first K chunk", i);
       NB_CHECK_ARG(k.row0 >= 0 && k.row0 % 8 == 0, "program op %d: row0=%d", i, k.row0);
       for (int c = 0; c < op.n_chunks; ++c)
         if ((op.blk_mask[c] >> b) & 1)

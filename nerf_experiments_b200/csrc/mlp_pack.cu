@@ -33,7 +33,8 @@ mlp_pack_kernel(const float* __restrict__ params, const NbPackChunk* __restrict_
         }
         w[h] = tc::pack_bf16(v[0], v[1]);
       }
-      *reinterpret_cast<uint4*>(dst + (size_t)r * 128u + ((uint32_t)(q ^ (r & 7)) << 4)) =
+      const int R = ch.dst_row0 + r * ch.dst_row_step;   // image row
+      *reinterpret_cast<uint4*>(dst + (size_t)R * 128u + ((uint32_t)(q ^ (R & 7)) << 4)) =
           make_uint4(w[0], w[1], w[2], w[3]);
     }
   } else if (d - n_chunks < n_biases) {

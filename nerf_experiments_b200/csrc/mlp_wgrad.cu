@@ -7,6 +7,10 @@
 // A persistent CTA accumulates its range in TMEM (2 x 256 fp32 columns) and flushes once with
 // red.global.add into the flat fp32 gradient buffer. HBM-bound by construction
 // (128 FLOP per byte of stash read).
+//
+// Bias gradients ride along: the four flush warps are idle while an item accumulates, so each
+// sums the columns of one dY half slab per pipeline stage while it sits in shared memory (the
+// item that carries bias_dst >= 0 for its dY slabs), fp32 in registers over the whole item.
 #include "common.cuh"
 #include "mlp.h"
 #include "tc.cuh"
@@ -48,7 +52,7 @@ mlp_wgrad_kernel(const __grid_constant__ WgradParams p) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < kWgStages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], 1 + 4);   // MMA commit + the four column-sum warps
     }
     mbar_init(acc_full, 1);
     mbar_init(acc_empty, 128);
@@ -121,12 +125,66 @@ mlp_wgrad_kernel(const __grid_constant__ WgradParams p) {
       }
     }
   } else {
-    // flush warps: TMEM lane = output feature within the 128-block
-    uint32_t f_phase = 0;
+    // flush warps: TMEM lane = output feature within the 128-block. While the item accumulates,
+    // warp w sums the columns of dY slab w of every stage (bias gradient).
+    uint32_t f_phase = 0, stage = 0, phase = 0;
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int rg = lane >> 3, pc = lane & 7;   // 16-row group of the half slab, physical 16-byte chunk
     for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
       const NbWgradItem item = p.items[it];
       const int n_mb = (item.n_dy_slabs + 1) / 2;
+      const bool sums = item.bias_dst >= 0 && warp < item.n_dy_slabs;
+      float bacc[8][8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) bacc[q][e] = 0.f;
+      for (int tile = item.tile_begin; tile < item.tile_end; ++tile) {
+        for (int half = 0; half < 2; ++half) {
+          mbar_wait(&full[stage], phase);
+          if (sums) {
+            const uint8_t* base = smem + stage * kStageBytes + (uint32_t)warp * kHalfSlabBytes +
+                                  (uint32_t)(rg * 16) * 128u + (uint32_t)pc * 16u;
+#pragma unroll
+            for (int r8 = 0; r8 < 2; ++r8) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {   // row & 7 == q: logical chunk pc ^ q
+                const uint4 v = *reinterpret_cast<const uint4*>(base + (uint32_t)(r8 * 8 + q) * 128u);
+                bacc[q][0] += __uint_as_float(v.x << 16); bacc[q][1] += __uint_as_float(v.x & 0xffff0000u);
+                bacc[q][2] += __uint_as_float(v.y << 16); bacc[q][3] += __uint_as_float(v.y & 0xffff0000u);
+                bacc[q][4] += __uint_as_float(v.z << 16); bacc[q][5] += __uint_as_float(v.z & 0xffff0000u);
+                bacc[q][6] += __uint_as_float(v.w << 16); bacc[q][7] += __uint_as_float(v.w & 0xffff0000u);
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[stage]);
+          if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+      if (sums) {
+        // lane (.., pc) holds in bacc[q] the partial sums of logical chunk pc ^ q: lane c gathers
+        // bacc[q] from lane c ^ q, then the four row groups are folded
+        float tot[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) tot[e] = bacc[0][e];
+#pragma unroll
+        for (int q = 1; q < 8; ++q)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) tot[e] += __shfl_xor_sync(0xffffffffu, bacc[q][e], q);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          tot[e] += __shfl_xor_sync(0xffffffffu, tot[e], 8);
+          tot[e] += __shfl_xor_sync(0xffffffffu, tot[e], 16);
+        }
+        if (rg == 0 && item.tile_end > item.tile_begin) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int m = warp * 64 + pc * 8 + e;
+            if (m < item.m_real) atomicAdd(p.d_params + item.bias_dst + m, tot[e]);
+          }
+        }
+      }
       mbar_wait(acc_full, f_phase);
       f_phase ^= 1u;
       tcgen05_fence_after();

@@ -153,4 +153,64 @@ __device__ __forceinline__ void pe_backward(const NbPeCfg& cfg, const float* mas
   }
 }
 
+// As pe_backward, for the 16-column quarter CQ of an accumulator in the canonical column order
+// (NB_PE_CANON_*, mlp.h) held in registers: every column index is a compile-time constant,
+// levels beyond cfg.levels are predicated off. The four quarters of a row add up to the full
+// gradient; the mean-shift scale (integrated PE) is returned by every quarter.
+template <int CQ>
+__device__ __forceinline__ void pe_backward_canon_quarter(const NbPeCfg& cfg, const float* mask,
+                                                          const PeSample& s, const uint32_t (&g)[16],
+                                                          float (&dx)[3], float& dir_scale) {
+  float x[3] = {s.x[0], s.x[1], s.x[2]};
+  PeIpe ipe;
+  dir_scale = 0.f;
+  if (cfg.kind == NB_PE_INTEGRATED) {
+    ipe = pe_ipe_prepare(cfg, s);
+    dir_scale = ipe.mu_diff;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) x[c] = x[c] + ipe.mu_diff * s.dir[c];
+  }
+  dx[0] = dx[1] = dx[2] = 0.f;
+  if (CQ == NB_PE_CANON_IDENTITY / 16 && (cfg.include_identity || cfg.kind == NB_PE_IDENTITY)) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) dx[c] = __uint_as_float(g[NB_PE_CANON_IDENTITY % 16 + c]);
+  }
+  if (cfg.kind == NB_PE_IDENTITY) return;
+  const int L = cfg.levels;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float sn = 0.f, cs = 1.f;
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < NB_PE_CANON_LEVELS; ++j) {
+      constexpr int kNone = -1;
+      const int col = 2 * (NB_PE_CANON_LEVELS * c + j);
+      const bool mine = (col / 16 == CQ);
+      // exact evaluation at the anchor level of a group this quarter needs, double-angle steps
+      // inside the group (as pe_encode)
+      const int anchor = (j / kPeAnchor) * kPeAnchor;
+      bool group_needed = false;
+#pragma unroll
+      for (int jj = 0; jj < kPeAnchor; ++jj)
+        if (anchor + jj < NB_PE_CANON_LEVELS && (2 * (NB_PE_CANON_LEVELS * c + anchor + jj)) / 16 == CQ) group_needed = true;
+      (void)kNone;
+      if (group_needed && j < L) {
+        const float freq = cfg.scale * (float)(1 << j);
+        if (j == anchor) sincosf(x[c] * freq, &sn, &cs);
+        if (mine) {
+          float w = mask[j];
+          if (cfg.kind == NB_PE_INTEGRATED) w *= __expf(-0.5f * ipe.var[c] * (float)(1 << (2 * j)));
+          const float g_cos = __uint_as_float(g[col % 16]);
+          const float g_sin = __uint_as_float(g[col % 16 + 1]);
+          acc += w * freq * (cs * g_sin - sn * g_cos);
+        }
+        const float s2 = 2.f * sn * cs;
+        cs = 1.f - 2.f * sn * sn;
+        sn = s2;
+      }
+    }
+    dx[c] += acc;
+  }
+}
+
 }  // namespace nerfb200

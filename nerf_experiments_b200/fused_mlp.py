@@ -101,7 +101,7 @@ class FusedField:
             all_chunks = list(cm.pack_chunks)
             units = cm.wpack_bytes // 1024
             for want in (False, True):
-                cb = compile_backward(cm, want)
+                cb = compile_backward(cm, want, self._encoders())
                 shift = units - cm.wpack_bytes // 1024
                 for ch in cb.pack_chunks:
                     ch.dst_off += shift
@@ -113,11 +113,11 @@ class FusedField:
                 all_chunks += cb.pack_chunks
                 self.bwd[want] = cb
             self.n_pack_chunks = len(all_chunks)
-            self.wpack = th.empty(max(units * 1024, 1024), device=device, dtype=th.uint8)
+            # zero-initialised: image rows no pack descriptor covers must read as zero weights
+            self.wpack = th.zeros(max(units * 1024, 1024), device=device, dtype=th.uint8)
             self.bias = th.zeros(max(cm.bias_floats, 1), device=device, dtype=th.float32)
             self.chunks_dev = to_device_array(all_chunks, NbPackChunk, device)
             self.biases_dev = to_device_array(cm.pack_biases, NbPackBias, device)
-            self.bias_map_dev = th.tensor(self.bwd[False].bias_map or [-1], device=device, dtype=th.int32)
             self._wgrad_items = {}
             self._packed_sig = None
         sig = self.flat.signature()
@@ -146,6 +146,15 @@ class FusedField:
         fwd = sum(L.lin.out_f * L.lin.in_f for L in self.compiled.layers)
         enc = sum(L.lin.out_f * s.width for L in self.compiled.layers for s in L.sources if s.kind != "act")
         return {"fwd": fwd, "bwd_inputs": fwd, "bwd": fwd - enc, "wgrad": fwd}
+
+    def _encoders(self):
+        out = {}
+        from .positional_encodings import IdentityPositionalEncoding
+        for kind, enc in (("pos", self.pe_pos), ("dir", self.pe_dir)):
+            identity_only = isinstance(enc, IdentityPositionalEncoding)
+            has_id = 1 if (identity_only or getattr(enc, "include_identity", False)) else 0
+            out[kind] = (0 if identity_only else int(enc.levels), has_id)
+        return out
 
     def pe_cfgs(self):
         cp = self.pe_pos.describe()
@@ -203,8 +212,8 @@ class FusedField:
         samples_mode = bool(inputs.pos)
         if want_input_grads:
             if samples_mode:
-                d_a = th.empty((n, 3), device=dev, dtype=th.float32)
-                d_b = th.empty((n, 3), device=dev, dtype=th.float32)
+                d_a = th.zeros((n, 3), device=dev, dtype=th.float32)   # the kernel accumulates (+=)
+                d_b = th.zeros((n, 3), device=dev, dtype=th.float32)
             else:
                 d_a = th.zeros((n_rays, 3), device=dev, dtype=th.float32)
                 d_b = th.zeros((n_rays, 3), device=dev, dtype=th.float32)
@@ -218,8 +227,7 @@ class FusedField:
                 cb.head_sigma_col3, cb.pos_grad_cols if want_input_grads else 0,
                 cb.dir_grad_cols if want_input_grads else 0,
                 None if samples_mode else _ptr(d_a), None if samples_mode else _ptr(d_b),
-                _ptr(d_a) if samples_mode else None, _ptr(d_b) if samples_mode else None,
-                cb.head_bias_off, cm.bias_floats, _ptr(self.bias_map_dev), _ptr(flat_grad), stream), "mlp_bwd"))
+                _ptr(d_a) if samples_mode else None, _ptr(d_b) if samples_mode else None, stream), "mlp_bwd"))
             items_dev, n_items = self._items(n_tiles)
             self._timed("mlp_wgrad", lambda: check(lib().nerfb200_mlp_wgrad(
                 _ptr(items_dev), n_items, _ptr(stash), cm.stash_slabs_per_tile, _ptr(dy_stash),

@@ -12,8 +12,7 @@ from ._lib import (NB_MAX_CHUNKS, NB_MAX_OPS, NbBlock, NbOp, NbPackBias, NbPackC
 
 SLAB_PE_POS = 4
 SLAB_PE_DIR = 5
-TMEM_EXTRA_COL = 256      # forward: density block; backward: position-encoding gradients
-TMEM_DIR_COL = 320        # backward: direction-encoding gradients
+TMEM_EXTRA_COL = 256      # forward: density block = column 0 of the OTHER accumulator buffer
 
 
 def _ceil(a: int, b: int) -> int:
@@ -266,6 +265,7 @@ class WgradUnit:
     n_real: int
     dst: int
     ld: int
+    bias_dst: int = -1     # float index of the bias gradient of the unit's first output feature
 
 
 @dataclass
@@ -286,7 +286,9 @@ def _out_chunks(L: LayerSpec) -> int:
     return 0 if L.act == "rgb" else _ceil(L.out_main, 64)
 
 
-def compile_backward(cm: CompiledMlp, want_input_grads: bool) -> CompiledBackward:
+def compile_backward(cm: CompiledMlp, want_input_grads: bool, encoders=None) -> CompiledBackward:
+    """encoders: {"pos": (levels, has_identity_columns), "dir": ...} — needed for the canonical
+    column order of the encoding-gradient accumulators (include/nerfb200_mlp.h)."""
     layers = cm.layers
     n_layers = len(layers)
     fprog = cm.program
@@ -305,7 +307,6 @@ def compile_backward(cm: CompiledMlp, want_input_grads: bool) -> CompiledBackwar
 
     prog = NbProgram()
     ops = []
-    seen = {"pos": 0, "dir": 0}
     grad_cols = {"pos": 0, "dir": 0}
     for l in range(n_layers - 1, -1, -1):
         L = layers[l]
@@ -349,12 +350,39 @@ def compile_backward(cm: CompiledMlp, want_input_grads: bool) -> CompiledBackwar
 
         if want_input_grads:
             for kind, c0, width in aux_srcs:
+                levels, has_id = encoders[kind]
+                if levels > _lib.PE_CANON_LEVELS or width != 3 * has_id + 6 * levels:
+                    raise RuntimeError(f"{kind} encoding ({levels} levels, width {width}) does not fit the "
+                                       "canonical gradient layout")
                 op = NbOp()
-                n_block = _ceil(width, 32) * 32
-                emit(op, c0, width, n_block, TMEM_EXTRA_COL if kind == "pos" else TMEM_DIR_COL, seen[kind])
-                seen[kind] = 1
-                grad_cols[kind] = max(grad_cols[kind], n_block)
-                op.epi = _lib.BEPI_NONE
+                n_block = _lib.PE_CANON_COLS
+                op.n_chunks = len(a_chunks)
+                for ci, (slab, k16, krow0, kcols) in enumerate(a_chunks):
+                    op.a_src[ci] = slab
+                    op.k16[ci] = k16
+                    op.w_rows[ci] = n_block
+                    op.w_off[ci] = w_units
+                    op.blk_mask[ci] = 1
+                    op.n_sub[ci] = 1
+                    base = lin.w_off + krow0 * lin.in_f + c0
+                    # image row = canonical column; rows no descriptor writes stay zero
+                    groups = []
+                    if has_id:
+                        groups.append((0, 3, _lib.PE_CANON_IDENTITY, 1))
+                    off = 3 * has_id
+                    for cc in range(3):
+                        groups.append((off + cc * levels, levels, 2 * _lib.PE_CANON_LEVELS * cc, 2))
+                        groups.append((off + 3 * levels + cc * levels, levels, 2 * _lib.PE_CANON_LEVELS * cc + 1, 2))
+                    for e0, n_e, row0, step in groups:
+                        if n_e > 0:
+                            chunks.append(NbPackChunk(base=base + e0, row_stride=1, col_stride=lin.in_f,
+                                                      n_rows=n_e, n_cols=kcols, rows_padded=n_e,
+                                                      dst_off=w_units, dst_row0=row0, dst_row_step=step))
+                    w_units += n_block // 8
+                op.n_blocks = 1
+                op.blocks[0] = NbBlock(0, n_block, 0, 0)
+                grad_cols[kind] = n_block
+                op.epi = _lib.BEPI_PEGRAD_POS if kind == "pos" else _lib.BEPI_PEGRAD_DIR
                 op.out_chunks = 0
                 op.bias_off = -1
                 op.stash_slab = -1
@@ -403,11 +431,14 @@ def compile_backward(cm: CompiledMlp, want_input_grads: bool) -> CompiledBackwar
                 x_slab, n_x = fprog.ops[l - 1].stash_slab, _ceil(src.width, 64)
             else:
                 x_slab, n_x = (0 if src.kind == "pos" else 1), 1
+            # the unit of a layer's first input source also carries the bias gradient
+            first = (col0 == 0)
             units.append(WgradUnit(dy_slab[l], n_main_slabs, x_slab, n_x, m_main, src.width,
-                                   lin.w_off + col0, lin.in_f))
+                                   lin.w_off + col0, lin.in_f, lin.b_off if first else -1))
             if L.sigma == "extra":
                 units.append(WgradUnit(dy_slab[l] + n_main_slabs, 1, x_slab, n_x, 1, src.width,
-                                       lin.w_off + L.out_main * lin.in_f + col0, lin.in_f))
+                                       lin.w_off + L.out_main * lin.in_f + col0, lin.in_f,
+                                       lin.b_off + L.out_main if first else -1))
             col0 += src.width
 
     head = layers[-1]
@@ -435,6 +466,6 @@ def schedule_wgrad(units: List[WgradUnit], n_tiles: int, n_workers: int):
                 items.append((c * (t1 - t0), NbWgradItem(tile_begin=t0, tile_end=t1, n_dy_slabs=u.n_dy_slabs,
                                                          n_x_slabs=u.n_x_slabs, dy_slab=u.dy_slab, x_slab=u.x_slab,
                                                          m_real=u.m_real, n_real=u.n_real, dst=u.dst, ld=u.ld,
-                                                         reserved=0)))
+                                                         bias_dst=u.bias_dst)))
     items.sort(key=lambda t: -t[0])
     return [it for _, it in items]

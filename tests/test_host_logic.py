@@ -85,12 +85,21 @@ def test_forward_program_of_the_standard_network():
     covered = sum(c.n_rows * c.n_cols for c in cm.pack_chunks)
     assert covered == sum(p.numel() for n, p in net.named_parameters() if n.endswith("weight"))
     assert sum(b.n for b in cm.pack_biases) == sum(p.numel() for n, p in net.named_parameters() if n.endswith("bias"))
-    cb = compile_backward(cm, True)
-    assert (cb.pos_grad_cols, cb.dir_grad_cols) == (64, 32)
+    cb = compile_backward(cm, True, f._encoders())
+    assert (cb.pos_grad_cols, cb.dir_grad_cols) == (64, 64)   # canonical encoding-gradient layout
+    # the transposed images of an encoding-gradient op cover every (output, encoding column) once,
+    # each at its canonical row: cos(c, j) -> 2*(10c+j), sin -> +1, identity -> 60..62
+    rows = {}
+    for c in cb.pack_chunks:
+        if c.dst_row_step == 2 or c.dst_row0 == 60:
+            rows.setdefault(c.dst_off, set()).update(c.dst_row0 + r * c.dst_row_step for r in range(c.n_rows))
+    assert rows and all(len(r) in (63, 27) and max(r) <= 62 for r in rows.values())
     # weight-gradient units tile every weight exactly once
     total = sum(u.m_real * u.n_real for u in cb.units)
     assert total == covered
-    assert sorted(set(cb.bias_map) - {-1}) == sorted(
+    # ... and every bias element is the column sum of exactly one unit's dY slabs
+    bias_idx = sorted(u.bias_dst + m for u in cb.units if u.bias_dst >= 0 for m in range(u.m_real))
+    assert bias_idx == sorted(
         i for n, p in net.named_parameters() if n.endswith("bias")
         for i in range(f.flat.offset_of(p), f.flat.offset_of(p) + p.numel()))
 
