@@ -193,6 +193,22 @@ int nerfb200_mlp_wgrad(const NbWgradItem* items_dev, int n_items, const void* x_
                        float* d_params, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * a6, a9. Learnable per-feature activations of the GARF / SARF / Gabor networks over (N, F)
+ * row-major fp32 activations. Replaces GaussActivation.forward/backward (barf/gaussian.py:8-34,
+ * == garf/gaussian.py), SarfAct.forward and its autograd (sarf/activation.py:63-65) and
+ * GaborActivation.forward/backward (gaborf/gabor.py:8-29).
+ *   p0: (F,) inverse standard deviation (GAUSS, GABOR: v = p0^2 + 1e-6) or frequency (SARF)
+ *   p1: (F,) spread (GABOR only, else NULL)
+ *   bwd: dx (N, F) is written; dp0 / dp1 (F,) accumulate (+=, caller zeroes) the gradients
+ *        w.r.t. the PARAMETERS p0 / p1 (the v = p0^2 + 1e-6 chain rule is applied inside).
+ */
+enum { NERFB200_ACT_GAUSS = 0, NERFB200_ACT_SARF = 1, NERFB200_ACT_GABOR = 2 };
+int nerfb200_act_fwd(int kind, const float* x, const float* p0, const float* p1, long long N,
+                     int F, float* y, void* stream);
+int nerfb200_act_bwd(int kind, const float* x, const float* p0, const float* p1, const float* g,
+                     long long N, int F, float* dx, float* dp0, float* dp1, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * K9. Fused Adam over the flat fp32 parameter buffer (torch.optim.Adam arithmetic, per-group
  * learning rate / weight decay), replacing the optimiser the reference configures at
  * barf/model_interpolation.py:543-564.  group_* are HOST arrays of n_groups entries

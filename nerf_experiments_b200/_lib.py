@@ -26,6 +26,7 @@ BEPI_MASK, BEPI_PLAIN, BEPI_PLAIN_SIGMA, BEPI_MASK_SIGMA, BEPI_NONE, BEPI_PEGRAD
 PE_CANON_LEVELS, PE_CANON_COLS, PE_CANON_IDENTITY = 10, 64, 60
 PE_IDENTITY, PE_FOURIER, PE_INTEGRATED = range(3)
 COMPOSITE_BARF, COMPOSITE_NERFACC = 0, 1
+ACT_GAUSS, ACT_SARF, ACT_GABOR = 0, 1, 2
 
 
 class NbBlock(C.Structure):
@@ -136,6 +137,8 @@ def _declare(L):
                                      C.c_longlong, f32, vp]
     L.nerfb200_pe_fwd.argtypes = [C.POINTER(NbPeCfg), vp, vp, vp, vp, vp, vp, C.c_longlong, vp, vp]
     L.nerfb200_pe_bwd.argtypes = [C.POINTER(NbPeCfg), vp, vp, vp, vp, vp, vp, vp, C.c_longlong, vp, vp, vp]
+    L.nerfb200_act_fwd.argtypes = [i32, vp, vp, vp, C.c_longlong, i32, vp, vp]
+    L.nerfb200_act_bwd.argtypes = [i32, vp, vp, vp, vp, C.c_longlong, i32, vp, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("nerfb200_last_error", "nerfb200_launch_count"):
@@ -149,7 +152,7 @@ EXPORTS = [
     "nerfb200_resample_alloc", "nerfb200_resample_fallback", "nerfb200_resample_icdf",
     "nerfb200_pose_fwd", "nerfb200_pose_bwd", "nerfb200_so3_to_SO3",
     "nerfb200_mlp_pack", "nerfb200_mlp_fwd", "nerfb200_mlp_bwd", "nerfb200_mlp_wgrad", "nerfb200_pe_fwd", "nerfb200_pe_bwd",
-    "nerfb200_adam_step",
+    "nerfb200_adam_step", "nerfb200_act_fwd", "nerfb200_act_bwd",
 ]
 
 

@@ -204,11 +204,11 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdParams p) {
           const float* bias_q = bias + 16 * cq;
           const uint32_t acc_q = acc + (uint32_t)(16 * cq);
           tmem_ld16(acc_q, va);
+          // the slabs are about to be rewritten: their stash copies must have drained
+          drain.acquire_ordered(sm.slab_drained, (1u << oc) - 1u, lane);
           auto finish = [&](int j, uint32_t bits) {
             const bool tr = threadIdx.x == 0 && oi == 2 && j == 1;
             NB_TRACE(385, tr);
-            // slab j is about to be rewritten: its stash copy must have drained
-            drain.acquire(sm.slab_drained, j, lane);
             NB_TRACE(386, tr);
             store_packed16(packed, sm.slab(j), row, cq);
             if (mask_out != nullptr) mask_out[(size_t)(2 * j) * NB_TILE_ROWS * 2] = (uint16_t)bits;

@@ -191,7 +191,11 @@ struct SlabTracker {
 // pending bit and one parity bit per slab suffice (no loops in the epilogue's hot path).
 struct DrainBits {
   uint32_t pending = 0, parity = 0;
-  __device__ __forceinline__ void produced(uint32_t mask) { pending |= mask; }
+  int last = -1;   // most recently published slab with a stash copy
+  __device__ __forceinline__ void produced(uint32_t mask) {
+    pending |= mask;
+    if (mask) last = 31 - __clz(mask);
+  }
   // warp-collective: lane 0 polls slab_drained[s] if a copy of slab s is outstanding
   __device__ __forceinline__ void acquire(uint64_t* bars, int s, int lane) {
     if ((pending >> s) & 1u) {
@@ -206,6 +210,20 @@ struct DrainBits {
       const int s = __ffs(mask) - 1;
       mask &= mask - 1u;
       acquire(bars, s, lane);
+    }
+  }
+  // The stash copies drain in the order the slabs were published, so when the most recently
+  // published slab is among those about to be rewritten, waiting for it covers the others: one
+  // barrier round trip per op instead of four.
+  __device__ __forceinline__ void acquire_ordered(uint64_t* bars, uint32_t mask, int lane) {
+    mask &= pending;
+    if (mask == 0u) return;
+    if (last >= 0 && ((mask >> last) & 1u)) {
+      tc::mbar_wait(&bars[last], (parity >> last) & 1u);
+      parity ^= mask;
+      pending &= ~mask;
+    } else {
+      acquire_mask(bars, mask, lane);
     }
   }
 };

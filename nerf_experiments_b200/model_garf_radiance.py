@@ -1,0 +1,68 @@
+"""GARF radiance network — module surface of reference garf/model_radiance.py:9-96
+(== barf/model_garf_radiance.py:9-113): same constructor, sub-module names (state-dict keys
+`model_density_1.{0..7}`, `model_density_2.{0..6}`, `model_color.{0..3}`), seeded initialisation,
+`parameters_linear()` / `parameters_gaussian()` and `forward(pos, dir) -> (rgb, density)`.
+
+Round-1 status: the Gaussian activations run in the CUDA kernels of csrc/activations.cu; the
+Linear layers are plain library GEMMs (cuBLAS through torch). The layers are up to 1024 wide,
+which does not fit the 256-column tile program of the fused kernel: fusing this
+network is the round-2 item. th.compile of the reference is dropped (no tracing compiler)."""
+from typing import Iterator
+
+import torch as th
+import torch.nn as nn
+
+from .gaussian import GaussAct
+
+
+class _GaussNetBase(nn.Module):
+    def __init__(self, gaussian_init_min: float, gaussian_init_max: float):
+        super().__init__()
+        self.gaussian_init_min = gaussian_init_min
+        self.gaussian_init_max = gaussian_init_max
+        self._parameters_linear: list = []
+        self._parameters_gaussian: list = []
+
+    def _create_linear(self, features_in: int, features_out: int) -> nn.Linear:
+        linear = nn.Linear(features_in, features_out)
+        self._parameters_linear.append(linear.weight)
+        self._parameters_linear.append(linear.bias)
+        return linear
+
+    def _create_gaussian(self, features_in) -> GaussAct:
+        act = GaussAct(features_in, self.gaussian_init_min, self.gaussian_init_max)
+        self._parameters_gaussian.append(act.inv_standard_deviation)
+        return act
+
+    def parameters_linear(self) -> Iterator[nn.Parameter]:
+        return iter(self._parameters_linear)
+
+    def parameters_gaussian(self) -> Iterator[nn.Parameter]:
+        return iter(self._parameters_gaussian)
+
+
+class RadianceNetwork(_GaussNetBase):
+    def __init__(self, gaussian_init_min: float, gaussian_init_max: float):
+        super().__init__(gaussian_init_min, gaussian_init_max)
+        # creation order = the reference's (it fixes the seeded initial values)
+        self.model_density_1 = nn.Sequential(
+            self._create_linear(3, 1024), self._create_gaussian(1024),
+            self._create_linear(1024, 256), self._create_gaussian(256),
+            self._create_linear(256, 128), self._create_gaussian(128),
+            self._create_linear(128, 128), self._create_gaussian(128))
+        self.model_density_2 = nn.Sequential(
+            self._create_linear(128 + 3, 512), self._create_gaussian(512),
+            self._create_linear(512, 256), self._create_gaussian(256),
+            self._create_linear(256, 128), self._create_gaussian(128),
+            self._create_linear(128, 128 + 1))
+        self.softplus = nn.Softplus(threshold=8)
+        self.model_color = nn.Sequential(
+            self._create_linear(128 + 3, 256), self._create_gaussian(256),
+            self._create_linear(256, 3), nn.Sigmoid())
+
+    def forward(self, pos: th.Tensor, dir: th.Tensor):
+        z1 = self.model_density_1(pos)
+        z2 = self.model_density_2(th.cat((z1, pos), dim=1))
+        density = self.softplus(z2[:, 128] - 1)
+        rgb = self.model_color(th.cat((z1[:, :128] + z2[:, :128], dir), dim=1))
+        return rgb, density

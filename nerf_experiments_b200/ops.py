@@ -230,3 +230,45 @@ class _Pose(th.autograd.Function):
 def pose_forward(rotation, translation, img_idx, o, d, grad_sink=None):
     """grad_sink: optional (d_rotation, d_translation) views the backward accumulates into."""
     return _Pose.apply(rotation, translation, img_idx, o, d, grad_sink)
+
+
+# ---------------------------------------------------------------------------------------------
+# a6 / a9 learnable activations (GARF Gaussian, SARF, Gabor)
+# ---------------------------------------------------------------------------------------------
+class _Activation(th.autograd.Function):
+    """y = act(x; p0[, p1]) over (N, F) activations with per-feature parameters; the backward
+    kernel returns dx and the row-reduced parameter gradients (what autograd's sum-to-shape does
+    in the reference, barf/gaussian.py:21-34, gaborf/gabor.py:19-29)."""
+
+    @staticmethod
+    def forward(ctx, kind, x, p0, p1):
+        shape = x.shape
+        F = shape[-1]
+        x2 = _f32(x.reshape(-1, F), "x")
+        p0c = _f32(p0.reshape(-1), "p0", (F,))
+        p1c = None if p1 is None else _f32(p1.reshape(-1), "p1", (F,))
+        y = th.empty_like(x2)
+        with th.cuda.device(x2.device):
+            check(lib().nerfb200_act_fwd(kind, _ptr(x2), _ptr(p0c), _ptr(p1c), x2.shape[0], F, _ptr(y),
+                                         _stream()), "act_fwd")
+        ctx.kind = kind
+        ctx.shape = shape
+        ctx.save_for_backward(x2, p0c, p1c)
+        return y.view(shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        x2, p0c, p1c = ctx.saved_tensors
+        F = x2.shape[1]
+        g2 = _f32(g.reshape(-1, F), "g")
+        dx = th.empty_like(x2)
+        dp0 = th.zeros_like(p0c)
+        dp1 = None if p1c is None else th.zeros_like(p1c)
+        with th.cuda.device(x2.device):
+            check(lib().nerfb200_act_bwd(ctx.kind, _ptr(x2), _ptr(p0c), _ptr(p1c), _ptr(g2), x2.shape[0], F,
+                                         _ptr(dx), _ptr(dp0), _ptr(dp1), _stream()), "act_bwd")
+        return None, dx.view(ctx.shape), dp0, dp1
+
+
+def activation(kind: int, x: th.Tensor, p0: th.Tensor, p1: Optional[th.Tensor] = None) -> th.Tensor:
+    return _Activation.apply(kind, x, p0, p1)

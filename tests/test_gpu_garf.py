@@ -1,0 +1,140 @@
+"""GPU parity of the GARF / SARF / Gabor path: the activation kernels (through the C ABI)
+against the fixtures of the unmodified reference, the GARF networks against the reference's
+outputs and gradients, and the GARF model chain (inverse-CDF sampling, nerfacc-flavour
+compositing, proposal loss) against the oracle restatement with identical uniforms."""
+import os
+
+import numpy as np
+import pytest
+import torch as th
+
+from oracle import ref_garf
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "garf.npz")
+THIN = 37
+
+
+def _g():
+    z = np.load(G)
+    return {k: th.from_numpy(z[k]) for k in z.files}
+
+
+def _thin(t):
+    return t if t.numel() <= 8192 else t.flatten()[::THIN]
+
+
+@pytest.mark.parametrize("name", ["gauss", "sarf", "gabor"])
+def test_activation_kernels_match_reference(cuda, name):
+    from nerf_experiments_b200 import _lib, ops
+    g = _g()
+    kind = {"gauss": _lib.ACT_GAUSS, "sarf": _lib.ACT_SARF, "gabor": _lib.ACT_GABOR}[name]
+    keys = {"gauss": ("gauss_p",), "sarf": ("sarf_p",), "gabor": ("gabor_p0", "gabor_p1")}[name]
+    x = g["act_x"].to(cuda).requires_grad_()
+    ps = [g[k].to(cuda).requires_grad_() for k in keys]
+    y = ops.activation(kind, x, *ps)
+    assert th.allclose(y.cpu(), g[name + "_y"], rtol=2e-6, atol=2e-7)
+    grads = th.autograd.grad(y, [x] + ps, g["act_up"].to(cuda))
+    assert th.allclose(grads[0].cpu(), g[name + "_dx"], rtol=2e-5, atol=2e-6)
+    gk = [name + "_dp"] if len(ps) == 1 else [name + "_dp0", name + "_dp1"]
+    for gr, k in zip(grads[1:], gk):
+        assert th.allclose(gr.cpu(), g[k], rtol=2e-4, atol=2e-5), k
+
+
+@pytest.mark.parametrize("N,F", [(1, 1), (5, 3), (1000, 129), (4096, 1024), (70000, 256)])
+def test_activation_kernels_shapes(cuda, N, F):
+    """Ragged shapes (F not a multiple of the block, one row, many row chunks) against the oracle."""
+    from nerf_experiments_b200 import _lib, ops
+    gen = th.Generator().manual_seed(N + F)
+    x = th.randn((N, F), generator=gen).requires_grad_()
+    p = (th.rand(F, generator=gen) + 0.5).requires_grad_()
+    up = th.randn((N, F), generator=gen)
+    y = ref_garf.gauss_act(x, p)
+    rx, rp = th.autograd.grad(y, (x, p), up)
+    xc, pc = x.detach().to(cuda).requires_grad_(), p.detach().to(cuda).requires_grad_()
+    yc = ops.activation(_lib.ACT_GAUSS, xc, pc)
+    gx, gp = th.autograd.grad(yc, (xc, pc), up.to(cuda))
+    assert th.allclose(yc.cpu(), y, rtol=2e-6, atol=2e-7)
+    assert th.allclose(gx.cpu(), rx, rtol=2e-5, atol=2e-6)
+    # the parameter gradient is a sum over N rows in a different order
+    assert th.allclose(gp.cpu(), rp, rtol=1e-3, atol=1e-4 * max(1.0, float(N) ** 0.5))
+
+
+def _seeded_nets(cuda):
+    from nerf_experiments_b200.model_garf_proposal import ProposalNetwork
+    from nerf_experiments_b200.model_garf_radiance import RadianceNetwork
+    th.manual_seed(77)
+    prop = ProposalNetwork(0.5, 1.5)
+    rad = RadianceNetwork(0.5, 1.5)
+    return prop.to(cuda), rad.to(cuda)
+
+
+def test_garf_networks_match_reference(cuda):
+    g = _g()
+    prop, rad = _seeded_nets(cuda)
+    th.backends.cuda.matmul.allow_tf32 = False
+    rgb, dens = rad(g["net_pos"].to(cuda), g["net_dir"].to(cuda))
+    assert th.allclose(rgb.cpu(), g["rad_rgb"], rtol=1e-4, atol=1e-5)
+    assert th.allclose(dens.cpu(), g["rad_density"], rtol=1e-4, atol=1e-5)
+    ((rgb * g["up_rgb"].to(cuda)).sum() + (dens * g["up_density"].to(cuda)).sum()).backward()
+    for n, p in rad.named_parameters():
+        ref = g["rad.grad." + n]
+        assert th.allclose(_thin(p.grad).cpu(), ref, rtol=5e-3, atol=2e-5 * float(ref.abs().max() + 1)), n
+    sp = prop(g["net_pos"].to(cuda))
+    assert th.allclose(sp.cpu(), g["prop_sigma"], rtol=1e-4, atol=1e-5)
+    (sp * g["up_prop"].to(cuda)).sum().backward()
+    for n, p in prop.named_parameters():
+        ref = g["prop.grad." + n]
+        assert th.allclose(_thin(p.grad).cpu(), ref, rtol=5e-3, atol=2e-5 * float(ref.abs().max() + 1)), n
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_garf_model_chain_matches_oracle(cuda, training):
+    from nerf_experiments_b200.model_garf import GarfModel
+    th.backends.cuda.matmul.allow_tf32 = False
+    th.manual_seed(3)
+    m = GarfModel(2.0, 7.0, 32, 48, 0.5, 1.5, 1.0, 1e-3, 1e-4, 100, 0.0, 1e-3, 1e-4, 100, 0.0).to(cuda)
+    m.train(training)
+    B = 24
+    gen = th.Generator().manual_seed(11)
+    o = th.nn.functional.normalize(th.randn((B, 3), generator=gen), dim=1) * 4.0
+    d = th.nn.functional.normalize(-o + 0.3 * th.randn((B, 3), generator=gen), dim=1)
+    target = th.rand((B, 3), generator=gen)
+    u = (th.rand(B, generator=gen), th.rand(B, generator=gen)) if training else None
+    sd_p = {k: v.detach().cpu().clone().requires_grad_() for k, v in m.proposal_network.state_dict().items()}
+    sd_r = {k: v.detach().cpu().clone().requires_grad_() for k, v in m.radiance_network.state_dict().items()}
+    r_rgb, r_op, r_dp, r_lp, (r0, r1) = ref_garf.garf_forward(
+        sd_p, sd_r, o, d, 2.0, 7.0, 32, 48, None if u is None else u[0], None if u is None else u[1])
+    uc = None if u is None else (u[0].to(cuda), u[1].to(cuda))
+    rgb, (lp, lr) = m._forward_loss((o.to(cuda), d.to(cuda), target.to(cuda)), uc)
+    _, opacity, depth, extras = m(o.to(cuda), d.to(cuda), uc)
+    # the sample intervals follow from bit-exact inverse-CDF resampling of a cdf that is itself
+    # the output of fp32 GEMMs: equal to a few ulp of t
+    assert th.allclose(extras["t_starts"].cpu(), r0, rtol=0, atol=2e-4)
+    assert th.allclose(rgb.cpu(), r_rgb, atol=2e-4)
+    assert th.allclose(opacity[:, 0].cpu(), r_op, atol=2e-4)
+    assert th.allclose(depth[:, 0].cpu(), r_dp, atol=2e-3)
+    assert float(lp) == pytest.approx(float(r_lp), rel=2e-2, abs=1e-7)
+    # gradients of the summed loss reach both networks like in the reference's manual optimisation
+    (lp + lr).backward()
+    r_loss = r_lp + th.nn.functional.mse_loss(r_rgb, target)
+    r_loss.backward()
+    for n, p in m.radiance_network.named_parameters():
+        ref = sd_r[n].grad
+        assert th.allclose(p.grad.cpu(), ref, rtol=2e-2, atol=3e-5 * float(ref.abs().max() + 1e-3)), n
+    for n, p in m.proposal_network.named_parameters():
+        ref = sd_p[n].grad
+        assert th.allclose(p.grad.cpu(), ref, rtol=5e-2, atol=5e-5 * float(ref.abs().max() + 1e-3)), n
+
+
+def test_garf_training_step_reduces_loss(cuda):
+    from nerf_experiments_b200.model_garf import GarfModel
+    th.manual_seed(5)
+    m = GarfModel(2.0, 7.0, 16, 32, 0.5, 1.5, 1.0, 1e-3, 1e-4, 1000, 0.0, 1e-3, 1e-4, 1000, 0.0).to(cuda)
+    m.train()
+    gen = th.Generator().manual_seed(1)
+    o = (th.nn.functional.normalize(th.randn((256, 3), generator=gen), dim=1) * 4.0).to(cuda)
+    d = th.nn.functional.normalize(-o.cpu() + 0.3 * th.randn((256, 3), generator=gen), dim=1).to(cuda)
+    target = th.full((256, 3), 0.25, device=cuda)
+    losses = [float(m.training_step((o, d, target), i)) for i in range(30)]
+    assert np.isfinite(losses).all() and np.mean(losses[-5:]) < np.mean(losses[:5])
