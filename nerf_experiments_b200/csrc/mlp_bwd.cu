@@ -116,7 +116,7 @@ mlp_bwd_kernel(const __grid_constant__ MlpBwdParams p) {
     const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     DrainBits drain;
     NB_TRACE_INIT();
-    uint32_t g_op = 0;
+    uint32_t g_op = 0, tile_phase = 0;
     const uint16_t* const masks16 = reinterpret_cast<const uint16_t*>(p.masks);
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long n_raw = (long long)tile * NB_TILE_ROWS + row;
@@ -125,6 +125,10 @@ mlp_bwd_kernel(const __grid_constant__ MlpBwdParams p) {
       // sign bits of this row: one 32-bit word per 32-column group, this thread owns half of it
       const uint16_t* tile_masks = masks16 + (((size_t)tile * p.fwd_mask_words_per_tile + (cq >> 1)) * NB_TILE_ROWS + row) * 2 + (cq & 1);
 
+      if (tile != (int)blockIdx.x) {   // the MMA warp has consumed every publication of the previous tile
+        mbar_wait(sm.tile_done, tile_phase);
+        tile_phase ^= 1u;
+      }
       // All MMAs of the previous tile are complete (its last accumulator was read); slab 0 may be
       // rewritten once its stash copy has drained.
       drain.acquire_mask(sm.slab_drained, sched.start_mask, lane);

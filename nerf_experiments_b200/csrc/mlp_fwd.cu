@@ -125,7 +125,7 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdParams p) {
     const FwdStashDst dst_of{p, sched};
     DrainBits drain;       // stash copies that must finish before a slab is rewritten
     NB_TRACE_INIT();
-    uint32_t g_op = 0;
+    uint32_t g_op = 0, tile_phase = 0;
     auto stashed = [&](int ph, uint32_t mask) {
       uint32_t out = 0u;
       for (uint32_t m = mask; m; m &= m - 1u) {
@@ -139,6 +139,10 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdParams p) {
       const long long n_raw = (long long)tile * NB_TILE_ROWS + row;
       const bool valid = n_raw < p.N;
       const long long n = valid ? n_raw : (long long)p.N - 1;
+      if (tile != (int)blockIdx.x) {   // the MMA warp has consumed every publication of the previous tile
+        mbar_wait(sm.tile_done, tile_phase);
+        tile_phase ^= 1u;
+      }
 
       // ---- positions and positional encodings: quarter 0 -> position slab; quarter 1 ->
       //      direction slab when it has one of its own (otherwise it shares slab 4 and is written

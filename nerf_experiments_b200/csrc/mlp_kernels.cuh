@@ -45,6 +45,7 @@ struct MlpSmem {
   uint64_t* slab_drained;  // [kMaxSlabs] stash warp -> row warps: the stash copy has read the slab
   uint64_t* acc_full;      // [2] MMA warp -> row warps: accumulator buffer complete
   uint64_t* tmem_free;     // [2] row warps -> MMA warp: accumulator buffer read out
+  uint64_t* tile_done;     // MMA warp -> row warps: every slab publication of the tile has been consumed
   uint32_t* tmem_ptr;
   float* mask_pos;         // [kMaxLevels]
   float* mask_dir;         // [kMaxLevels]
@@ -60,7 +61,8 @@ struct MlpSmem {
     slab_drained = slab_ready + kMaxSlabs;
     acc_full = slab_drained + kMaxSlabs;
     tmem_free = acc_full + 2;
-    tmem_ptr = reinterpret_cast<uint32_t*>(tmem_free + 2);
+    tile_done = tmem_free + 2;
+    tmem_ptr = reinterpret_cast<uint32_t*>(tile_done + 1);
     mask_pos = reinterpret_cast<float*>(c + 256);
     mask_dir = mask_pos + kMaxLevels;
     floats = reinterpret_cast<float*>(c + kCtrlBytes);
@@ -82,6 +84,7 @@ struct MlpSmem {
       tc::mbar_init(&acc_full[b], 1);
       tc::mbar_init(&tmem_free[b], kRowWarps);
     }
+    tc::mbar_init(tile_done, 1);
     tc::fence_barrier_init();
   }
 };
@@ -438,6 +441,14 @@ __device__ __forceinline__ void mma_issuer_loop(const NbProgram& prog, const Til
       __syncwarp();
       ++g_op;
     }
+    // A waiter must never fall two phases behind an mbarrier: the slabs the last op published
+    // (possibly read by no MMA) are consumed here, and only then may the row warps publish the
+    // next tile's first slabs (tile_done).
+    trk.produced(carry);
+    carry = 0u;
+    trk.acquire_all(sm.slab_ready);
+    if (elected) tc::mbar_arrive(sm.tile_done);
+    __syncwarp();
   }
 }
 

@@ -179,3 +179,11 @@ def test_fused_backward_standard(cuda):
     (0, 64, True, False, 1, True, True), (1, 100, True, False, 2, True, True)])
 def test_fused_backward_variants(cuda, n_hidden, hidden, ddir, ddens, nseg, identity, inp):
     _check_grads(_grad_case(cuda, 300, n_hidden, hidden, ddir, ddens, nseg, identity, inp, seed=2))
+
+
+@pytest.mark.parametrize("inp", [False, True])
+def test_fused_backward_many_tiles_per_cta(cuda, inp):
+    """More tiles than SMs (every CTA walks several tiles): the slab hand-off protocol across
+    tile boundaries, with and without the encoding-gradient ops (without them the last op of a
+    tile publishes slabs no MMA reads — the case that once ran two barrier phases ahead)."""
+    _check_grads(_grad_case(cuda, 128 * 400 + 5, 2, 128, True, False, 2, True, inp, seed=4))
