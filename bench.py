@@ -204,8 +204,19 @@ def run_ours(args):
         kernels[name] = {"ms": tms, "tflops": flops / (tms * 1e-3) / 1e12, "flops_per_launch": flops}
     top = max(kernels, key=lambda k: kernels[k]["ms"])
     peak = peaks["bf16_tflops_sustained"]
+    # DRAM traffic of the same kernel per launch, from the committed `ncu --set full` capture of
+    # this workload (profiles/r1_traffic.json; dram__bytes_read.sum + dram__bytes_write.sum)
+    traffic = None
+    try:
+        prof = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")))
+        kname = {"mlp_fwd_train": "mlp_fwd_kernel", "mlp_bwd_inputs": "mlp_bwd_kernel", "mlp_bwd": "mlp_bwd_kernel",
+                 "mlp_wgrad": "mlp_wgrad_kernel"}[top]
+        rec = prof["kernels"][kname]
+        traffic = rec["dram_bytes_read"] + rec["dram_bytes_write"]
+    except Exception:  # noqa: BLE001 - the capture is optional
+        traffic = None
     roofline = {"kernel": top, "bound": "tensor", "achieved": round(kernels[top]["tflops"], 2), "peak": peak,
-                "unit": "TFLOP/s", "frac": round(kernels[top]["tflops"] / peak, 4), "traffic": None,
+                "unit": "TFLOP/s", "frac": round(kernels[top]["tflops"] / peak, 4), "traffic": traffic,
                 "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)",
                 "kernels": {k: {"ms": round(v["ms"], 4), "tflops": round(v["tflops"], 2),
                                 "frac": round(v["tflops"] / peak, 4)} for k, v in kernels.items()},
