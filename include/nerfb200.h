@@ -209,6 +209,25 @@ int nerfb200_act_bwd(int kind, const float* x, const float* p0, const float* p1,
                      long long N, int F, float* dx, float* dp0, float* dp1, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * GPU-resident ray batcher. Replaces
+ * ImagePoseDataset.__getitem__ + DataLoader collate + H2D copy (barf/dataset.py:613-637; ray
+ * generation :407-482) and ImagePoseDataModule.get_blurred_pixel_colors
+ * (barf/data_module.py:276-369).
+ *   ray_index (B) int64: flat index image * H*W + pixel;  c2w_raw / c2w_noisy (N,4,4) row-major;
+ *   images (N, H*W, n_sigmas, 3) fp32;  image_id_map (N) int32 or NULL (identity).
+ *   blur_low < 0: colors (B, n_sigmas, 3) = the stored pyramid;
+ *   otherwise colors (B,2,3): [:,0] = c[blur_low]*blur_coef + c[blur_high]*(1-blur_coef),
+ *                             [:,1] = c[n_sigmas-1] (the unblurred pixel).
+ *   Outputs: o_raw, o_noisy, d_raw, d_noisy (B,3) fp32, img_idx (B) int64, pixel_width_out (B).
+ */
+int nerfb200_ray_batch(const long long* ray_index, int B, const float* c2w_raw,
+                       const float* c2w_noisy, const float* images, const int* image_id_map,
+                       int n_images, int H, int W, int n_sigmas, float focal, float pixel_width,
+                       int blur_low, int blur_high, float blur_coef, float* o_raw, float* o_noisy,
+                       float* d_raw, float* d_noisy, float* colors, long long* img_idx,
+                       float* pixel_width_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * K9. Fused Adam over the flat fp32 parameter buffer (torch.optim.Adam arithmetic, per-group
  * learning rate / weight decay), replacing the optimiser the reference configures at
  * barf/model_interpolation.py:543-564.  group_* are HOST arrays of n_groups entries
