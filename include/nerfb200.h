@@ -228,6 +228,17 @@ int nerfb200_ray_batch(const long long* ray_index, int B, const float* c2w_raw,
                        float* pixel_width_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Pose alignment on the device. Replaces
+ * CameraCalibrationModel.kabsch_algorithm and compute_pose_error
+ * (barf/model_camera_calibration.py:69-156, :340-346).
+ *   from, to (n,3) fp32, n <= 2048.  R (3,3), t (3), c (1):  to ~= c * R from + t.
+ *   remove_outliers: refit on the points closer than the 0.9 distance quantile of a first fit.
+ *   out_err (1) or NULL: mean |c R from + t - to| over all points with the final fit.
+ */
+int nerfb200_kabsch(const float* from, const float* to, int n, int remove_outliers, float* out_R,
+                    float* out_t, float* out_c, float* out_err, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * K9. Fused Adam over the flat fp32 parameter buffer (torch.optim.Adam arithmetic, per-group
  * learning rate / weight decay), replacing the optimiser the reference configures at
  * barf/model_interpolation.py:543-564.  group_* are HOST arrays of n_groups entries

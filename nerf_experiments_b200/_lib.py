@@ -141,6 +141,7 @@ def _declare(L):
     L.nerfb200_act_bwd.argtypes = [i32, vp, vp, vp, vp, C.c_longlong, i32, vp, vp, vp, vp]
     L.nerfb200_ray_batch.argtypes = [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, i32, i32, f32,
                                      vp, vp, vp, vp, vp, vp, vp, vp]
+    L.nerfb200_kabsch.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("nerfb200_last_error", "nerfb200_launch_count"):
@@ -154,7 +155,7 @@ EXPORTS = [
     "nerfb200_resample_alloc", "nerfb200_resample_fallback", "nerfb200_resample_icdf",
     "nerfb200_pose_fwd", "nerfb200_pose_bwd", "nerfb200_so3_to_SO3",
     "nerfb200_mlp_pack", "nerfb200_mlp_fwd", "nerfb200_mlp_bwd", "nerfb200_mlp_wgrad", "nerfb200_pe_fwd", "nerfb200_pe_bwd",
-    "nerfb200_adam_step", "nerfb200_act_fwd", "nerfb200_act_bwd", "nerfb200_ray_batch",
+    "nerfb200_adam_step", "nerfb200_act_fwd", "nerfb200_act_bwd", "nerfb200_ray_batch", "nerfb200_kabsch",
 ]
 
 

@@ -272,3 +272,26 @@ class _Activation(th.autograd.Function):
 
 def activation(kind: int, x: th.Tensor, p0: th.Tensor, p1: Optional[th.Tensor] = None) -> th.Tensor:
     return _Activation.apply(kind, x, p0, p1)
+
+
+# ---------------------------------------------------------------------------------------------
+# pose alignment (Kabsch with outlier rejection) and pose error — SURVEY.md §8f rank 4
+# ---------------------------------------------------------------------------------------------
+def kabsch(point_cloud_from: th.Tensor, point_cloud_to: th.Tensor, remove_outliers: bool = True,
+           want_error: bool = False):
+    """R (3,3), t (1,3), c (1,) with  to ~= c * R from + t  — the convention of
+    CameraCalibrationModel.kabsch_algorithm (barf/model_camera_calibration.py:69-156); one launch,
+    no host synchronisation. With want_error also the mean alignment error (compute_pose_error)."""
+    if point_cloud_from.shape != point_cloud_to.shape or point_cloud_from.dim() != 2 or point_cloud_from.shape[1] != 3:
+        raise ValueError("point_cloud_from and point_cloud_to must both be of shape (N, 3)")
+    a = _f32(point_cloud_from.detach(), "point_cloud_from")
+    b = _f32(point_cloud_to.detach(), "point_cloud_to")
+    dev = a.device
+    R = th.empty((3, 3), device=dev)
+    t = th.empty((1, 3), device=dev)
+    c = th.empty((1,), device=dev)
+    err = th.empty((1,), device=dev) if want_error else None
+    with th.cuda.device(dev):
+        check(lib().nerfb200_kabsch(_ptr(a), _ptr(b), a.shape[0], int(bool(remove_outliers)), _ptr(R), _ptr(t),
+                                    _ptr(c), _ptr(err), _stream()), "kabsch")
+    return (R, t, c, err[0]) if want_error else (R, t, c)

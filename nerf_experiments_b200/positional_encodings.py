@@ -146,6 +146,7 @@ class BarfPositionalEncoding(PositionalEncoding):
             value = float(self.levels)
         # in place: keeps the device pointer the kernels (and CUDA graphs) hold
         self.alpha.fill_(float(value))
+        self.alpha_value = float(value)     # host copy: schedules that depend on alpha need no device sync
 
     def compute_mask(self, alpha: th.Tensor) -> th.Tensor:
         k = th.arange(self.levels, device=alpha.device, dtype=th.float32)

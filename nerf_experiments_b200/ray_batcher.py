@@ -93,6 +93,23 @@ class GpuRayBatcher:
                 img_idx.data_ptr(), pw.data_ptr(), th.cuda.current_stream().cuda_stream), "ray_batch")
         return o_r, o_n, d_r, d_n, colors, img_idx, pw
 
+    # -- datamodule / dataset surface the calibration models read ----------------------------------
+    @property
+    def dataset_train(self):
+        return self
+
+    def get_blurred_pixel_colors(self, batch, sigma: float):
+        """ImagePoseDataModule.get_blurred_pixel_colors on an assembled batch whose colours are the
+        raw pyramid (B, n_sigmas, 3): returns the batch with colours (B, 2, 3) = [blurred, original].
+        (`batch(idx, sigma)` fuses this into the gather; this form serves callers that already hold
+        a batch.)"""
+        o_r, o_p, d_r, d_p, colors, img_idx, pw = batch
+        if colors.shape[1] == 2 and self.n_sigmas != 2:
+            return batch                                    # already interpolated by batch(idx, sigma)
+        lo, hi, coef = self.blur_levels(sigma)
+        blurred = colors[:, lo] * coef + colors[:, hi] * (1 - coef) if lo != hi else colors[:, lo]
+        return o_r, o_p, d_r, d_p, th.stack([blurred, colors[:, -1]], dim=1), img_idx, pw
+
     def __getitem__(self, index: int):
         """One ray, the reference's DatasetOutput (dataset.py:613-637)."""
         o_r, o_n, d_r, d_n, c, i, pw = self.batch(th.tensor([index], device=self.device))
