@@ -9,7 +9,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnerfb200.so")
+# NERFB200_LIB: another build of the same library (A/B timing of kernel experiments, scripts/ only)
+LIB_PATH = os.environ.get("NERFB200_LIB") or os.path.join(_HERE, "libnerfb200.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 # ---- mirrors of csrc/mlp.h -----------------------------------------------------------------

@@ -68,14 +68,14 @@ __device__ __forceinline__ void grad_math16(const uint32_t (&v)[16], uint32_t bi
     packed[i >> 1] = pack_bf16(a, b);
   }
 }
-// ... and the two swizzled 16-byte stores of (row, column quarter cq)
-__device__ __forceinline__ void store_packed16(const uint32_t (&packed)[8], uint8_t* slab, int row, int cq) {
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const uint32_t off = (uint32_t)row * 128u + ((uint32_t)((2 * cq + q) ^ (row & 7)) << 4);
-    *reinterpret_cast<uint4*>(slab + off) =
-        make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
-  }
+// ... and the two swizzled 16-byte stores of (row, column quarter cq): the thread's two chunk
+// addresses inside slab 0 are computed once per kernel, the slab index is an immediate offset
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void store_packed16(const uint32_t (&packed)[8], uint32_t sts0, uint32_t sts1, int j) {
+  sts128(sts0 + (uint32_t)j * NB_SLAB_BYTES, packed[0], packed[1], packed[2], packed[3]);
+  sts128(sts1 + (uint32_t)j * NB_SLAB_BYTES, packed[4], packed[5], packed[6], packed[7]);
 }
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
@@ -114,6 +114,10 @@ mlp_bwd_kernel(const __grid_constant__ MlpBwdParams p) {
     const int row = threadIdx.x & kTileRowMask;
     const int cq = threadIdx.x >> 7;                    // which 16-column quarter of every slab
     const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    uint32_t sts0 = smem_u32(sm.slab(0)) + (uint32_t)row * 128u + ((uint32_t)((2 * cq) ^ (row & 7)) << 4);
+    uint32_t sts1 = smem_u32(sm.slab(0)) + (uint32_t)row * 128u + ((uint32_t)((2 * cq + 1) ^ (row & 7)) << 4);
+    // opaque to the compiler: otherwise it rematerialises both addresses per slab
+    asm volatile("" : "+r"(sts0), "+r"(sts1));
     DrainBits drain;
     NB_TRACE_INIT();
     uint32_t g_op = 0, tile_phase = 0;
@@ -191,9 +195,9 @@ mlp_bwd_kernel(const __grid_constant__ MlpBwdParams p) {
           tmem_ld16(acc_q, va);
           drain.acquire_ordered(sm.slab_drained, (1u << oc) - 1u, lane);   // stash copies of the slabs have drained
           auto finish = [&](int j) {
-            store_packed16(packed, sm.slab(j), row, cq);
+            store_packed16(packed, sts0, sts1, j);
             signal_slab(sm.slab_ready, j, lane);
-            drain.produced(will_stash << j);
+            if (will_stash) { drain.pending |= 1u << j; drain.last = j; }
           };
 #pragma unroll
           for (int j = 0; j < 4; j += 2) {

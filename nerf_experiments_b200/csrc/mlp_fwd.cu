@@ -10,6 +10,7 @@
 // to the HBM stash (training). Consecutive layers alternate between two TMEM accumulator
 // buffers and hand activations over slab by slab, so the tensor pipe works on layer l+1 while
 // the row threads are still in the epilogue of layer l (see mlp_kernels.cuh).
+#include <type_traits>
 #include "common.cuh"
 #include "mlp.h"
 #include "mlp_kernels.cuh"
@@ -37,17 +38,22 @@ struct FwdStashDst {
 };
 
 // One 16-column group of an activation epilogue: bias, ReLU + sign bits, bf16 pack.
-// Returns the sign half-word: bit i set <=> pre-activation i is not negative.
+// Returns the sign half-word: bit i set <=> pre-activation i is not negative. The epilogue is
+// bound by the number of instructions the four row warps of a scheduler issue per slab, so
+// ReLU rides in the convert (cvt.rn.relu.bf16x2.f32) and each sign bit costs one funnel shift.
 template <bool kRelu>
 __device__ __forceinline__ uint32_t act_math16(const uint32_t (&v)[16], const float* bias16,
                                                uint32_t (&packed)[8]) {
   // two independent sign chains (one long funnel-shift chain is latency bound): chain c collects
   // elements 8c..8c+7, the first element ends up in the highest of its 8 bits
   uint32_t neg[2] = {0u, 0u};
-  const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
   for (int i = 0; i < 16; i += 4) {
+#ifdef NB_EXP_NOBIAS
+    const float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+#else
     const float4 bq = *reinterpret_cast<const float4*>(bias16 + i);
+#endif
     const float a0 = __uint_as_float(v[i]) + bq.x, a1 = __uint_as_float(v[i + 1]) + bq.y;
     const float a2 = __uint_as_float(v[i + 2]) + bq.z, a3 = __uint_as_float(v[i + 3]) + bq.w;
     if (kRelu) {
@@ -56,28 +62,26 @@ __device__ __forceinline__ uint32_t act_math16(const uint32_t (&v)[16], const fl
       n = __funnelshift_l(__float_as_uint(a1), n, 1);
       n = __funnelshift_l(__float_as_uint(a2), n, 1);
       n = __funnelshift_l(__float_as_uint(a3), n, 1);
+      asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(packed[i >> 1]) : "f"(a1), "f"(a0));
+      asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(packed[(i >> 1) + 1]) : "f"(a3), "f"(a2));
+    } else {
+      packed[i >> 1] = pack_bf16(a0, a1);
+      packed[(i >> 1) + 1] = pack_bf16(a2, a3);
     }
-    __nv_bfloat162 p0 = __floats2bfloat162_rn(a0, a1), p1 = __floats2bfloat162_rn(a2, a3);
-    if (kRelu) {   // on the packed pairs: half the instructions of an fp32 max
-      p0 = __hmax2(p0, zero);
-      p1 = __hmax2(p1, zero);
-    }
-    packed[i >> 1] = *reinterpret_cast<uint32_t*>(&p0);
-    packed[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&p1);
   }
   if (!kRelu) return 0xffffu;
   // element i sits at bit 15 - i of the merged half-word; reverse to bit i
   const uint32_t merged = ((neg[0] & 0xffu) << 8) | (neg[1] & 0xffu);
   return (~(__brev(merged) >> 16)) & 0xffffu;
 }
-// the two swizzled 16-byte stores of (row, column quarter cq)
-__device__ __forceinline__ void store_packed16(const uint32_t (&packed)[8], uint8_t* slab, int row, int cq) {
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const uint32_t off = (uint32_t)row * 128u + ((uint32_t)((2 * cq + q) ^ (row & 7)) << 4);
-    *reinterpret_cast<uint4*>(slab + off) =
-        make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
-  }
+// the two swizzled 16-byte stores of (row, column quarter cq): the thread's two chunk addresses
+// inside slab 0 are computed once per kernel, the slab index is an immediate offset
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void store_packed16(const uint32_t (&packed)[8], uint32_t sts0, uint32_t sts1, int j) {
+  sts128(sts0 + (uint32_t)j * NB_SLAB_BYTES, packed[0], packed[1], packed[2], packed[3]);
+  sts128(sts1 + (uint32_t)j * NB_SLAB_BYTES, packed[4], packed[5], packed[6], packed[7]);
 }
 
 __global__ void __launch_bounds__(kFwdThreads, 1)
@@ -122,6 +126,10 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdParams p) {
     const int row = threadIdx.x & kTileRowMask;         // tile row
     const int cq = threadIdx.x >> 7;                    // which 16-column quarter of every slab
     const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    uint32_t sts0 = smem_u32(sm.slab(0)) + (uint32_t)row * 128u + ((uint32_t)((2 * cq) ^ (row & 7)) << 4);
+    uint32_t sts1 = smem_u32(sm.slab(0)) + (uint32_t)row * 128u + ((uint32_t)((2 * cq + 1) ^ (row & 7)) << 4);
+    // opaque to the compiler: otherwise it rematerialises both addresses (12 instructions) per slab
+    asm volatile("" : "+r"(sts0), "+r"(sts1));
     const FwdStashDst dst_of{p, sched};
     DrainBits drain;       // stash copies that must finish before a slab is rewritten
     NB_TRACE_INIT();
@@ -210,36 +218,37 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdParams p) {
           tmem_ld16(acc_q, va);
           // the slabs are about to be rewritten: their stash copies must have drained
           drain.acquire_ordered(sm.slab_drained, (1u << oc) - 1u, lane);
+          uint32_t sign_bits[4];
           auto finish = [&](int j, uint32_t bits) {
-            const bool tr = threadIdx.x == 0 && oi == 2 && j == 1;
-            NB_TRACE(385, tr);
-            NB_TRACE(386, tr);
-            store_packed16(packed, sm.slab(j), row, cq);
-            if (mask_out != nullptr) mask_out[(size_t)(2 * j) * NB_TILE_ROWS * 2] = (uint16_t)bits;
-            NB_TRACE(387, tr);
+            store_packed16(packed, sts0, sts1, j);
+            sign_bits[j] = bits;    // stored after the last slab has been published: a global store in
+                                    // flight makes the proxy fence (MEMBAR.ALL.CTA) wait for its ack
             fence_proxy_async();
-            NB_TRACE(388, tr);
             __syncwarp();
-            NB_TRACE(389, tr);
             if (lane == 0) mbar_arrive(&sm.slab_ready[j]);
-            NB_TRACE(390, tr);
-            drain.produced(will_stash << j);
+            if (will_stash) { drain.pending |= 1u << j; drain.last = j; }
           };
+          auto run = [&](auto relu_tag) {
+            constexpr bool kRelu = decltype(relu_tag)::value;
 #pragma unroll
-          for (int j = 0; j < 4; j += 2) {
-            if (j < oc) {
-              tmem_ld_wait16(va);
-              if (j + 1 < oc) tmem_ld16(acc_q + (uint32_t)(64 * (j + 1)), vb);
-              finish(j, relu ? act_math16<true>(va, bias_q + 64 * j, packed) : act_math16<false>(va, bias_q + 64 * j, packed));
+            for (int j = 0; j < 4; j += 2) {
+              if (j < oc) {
+                tmem_ld_wait16(va);
+                if (j + 1 < oc) tmem_ld16(acc_q + (uint32_t)(64 * (j + 1)), vb);
+                finish(j, act_math16<kRelu>(va, bias_q + 64 * j, packed));
+              }
+              if (j + 1 < oc) {
+                tmem_ld_wait16(vb);
+                if (j + 2 < oc) tmem_ld16(acc_q + (uint32_t)(64 * (j + 2)), va);
+                finish(j + 1, act_math16<kRelu>(vb, bias_q + 64 * (j + 1), packed));
+              }
             }
-            if (j + 1 < oc) {
-              NB_TRACE(383, threadIdx.x == 0 && oi == 2 && j == 0);
-              tmem_ld_wait16(vb);
-              NB_TRACE(384, threadIdx.x == 0 && oi == 2 && j == 0);
-              if (j + 2 < oc) tmem_ld16(acc_q + (uint32_t)(64 * (j + 2)), va);
-              finish(j + 1, relu ? act_math16<true>(vb, bias_q + 64 * (j + 1), packed)
-                                 : act_math16<false>(vb, bias_q + 64 * (j + 1), packed));
-            }
+          };
+          if (relu) run(std::true_type{}); else run(std::false_type{});
+          if (mask_out != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (j < oc) mask_out[(size_t)(2 * j) * NB_TILE_ROWS * 2] = (uint16_t)sign_bits[j];
           }
         } else if (cq == 0) {
           // NB_EPI_RGB / NB_EPI_RGB_SIGMA: first 16 accumulator columns hold the outputs

@@ -324,7 +324,8 @@ __device__ __forceinline__ void encode_to_slab(const NbPeCfg& cfg, const float* 
 // clock64() stamps of its second tile, 4 per op: [buffer free seen, MMAs issued, acc_full seen,
 // epilogue done].
 static __device__ long long* g_trace = nullptr;
-// every role loads the pointer once (`NB_TRACE_INIT(tile0)`), block 0 traces its second tile
+#ifdef NB_ENABLE_TRACE
+// every role loads the pointer once (`NB_TRACE_INIT()`), block 0 traces its second tile
 #define NB_TRACE_INIT()                                                                         \
   long long* const nb_trace_ptr = (blockIdx.x == 0) ? *(long long* volatile*)&g_trace : nullptr; \
   const int nb_trace_tile = (int)(blockIdx.x + gridDim.x)
@@ -332,6 +333,12 @@ static __device__ long long* g_trace = nullptr;
   do {                                                                                \
     if (nb_trace_ptr != nullptr && tile == nb_trace_tile && (cond)) nb_trace_ptr[(slot)] = clock64(); \
   } while (0)
+#else
+// production builds carry no trace code: the stamps cost ~15 % of the epilogue's instructions.
+// scripts/trace_mlp.py runs against a build made with EXTRA=-DNB_ENABLE_TRACE.
+#define NB_TRACE_INIT() do { } while (0)
+#define NB_TRACE(slot, cond) do { } while (0)
+#endif
 
 // ---- warp-specialised loops shared by the forward and backward-data kernels ------------------
 // Weight producer (one thread): streams every weight image of the program, tile after tile,

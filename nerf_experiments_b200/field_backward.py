@@ -19,7 +19,7 @@ def field_backward(ctx, g_sigma, g_rgb):
         inputs = make_inputs(n, ctx.S, ctx.t_mode, ray_o=a, ray_d=b, t_start=t_start, t_end=t_end,
                              pixel_width=pixel_width, pixel_width_per_sample=False)
         n_rays = a.shape[0]
-    want_inputs = ctx.needs_input_grad[4] or ctx.needs_input_grad[5]
+    want_inputs = ctx.needs_input_grad[5] or ctx.needs_input_grad[6]
     g_sigma = None if g_sigma is None else g_sigma.contiguous().float()
     g_rgb = None if g_rgb is None else g_rgb.contiguous().float()
     flat_grad, d_a, d_b = field.backward(inputs, n, sigma, rgb, g_sigma, g_rgb, ctx.stash, ctx.masks,
@@ -27,12 +27,12 @@ def field_backward(ctx, g_sigma, g_rgb):
     ctx.stash = ctx.masks = None
     field.flat.last_grad = flat_grad
     if field.flat.grad_sink is not None:
-        param_grads = tuple(None for _ in ctx.needs_input_grad[9:])     # engine mode
+        param_grads = tuple(None for _ in ctx.needs_input_grad[10:])     # engine mode
     else:
         offs = [field.flat.offset_of(p) for p in field.own_params]
         param_grads = tuple(flat_grad[o:o + p.numel()].view(p.shape) if need else None
-                            for p, o, need in zip(field.own_params, offs, ctx.needs_input_grad[9:]))
-    return (None, None, None, None,
-            d_a if ctx.needs_input_grad[4] else None,
-            d_b if ctx.needs_input_grad[5] else None,
+                            for p, o, need in zip(field.own_params, offs, ctx.needs_input_grad[10:]))
+    return (None, None, None, None, None,
+            d_a if ctx.needs_input_grad[5] else None,
+            d_b if ctx.needs_input_grad[6] else None,
             None, None, None) + param_grads

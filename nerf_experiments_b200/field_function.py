@@ -22,13 +22,12 @@ class _FieldFunction(th.autograd.Function):
     NerfModel.forward signature) or "rays" (o, d per ray + t bins per sample)."""
 
     @staticmethod
-    def forward(ctx, model, mode, S, t_mode, a, b, t_start, t_end, pixel_width, *params):
+    def forward(ctx, model, mode, S, t_mode, training, a, b, t_start, t_end, pixel_width, *params):
         dev = a.device
         if not a.is_cuda:
             raise RuntimeError("the fused field runs on CUDA only (nerfb200 has no CPU fallback)")
         field = model.fused_field()
         field.prepare(dev)
-        training = any(ctx.needs_input_grad)   # grad mode is off inside Function.forward
         if mode == "samples":
             n = a.shape[0]
             inputs = make_inputs(n, 1, 0, pos=a, dir=b, t_start=t_start, t_end=t_end,
@@ -49,6 +48,12 @@ class _FieldFunction(th.autograd.Function):
         return field_backward(ctx, g_sigma, g_rgb)
 
 
+def _tracking(tensors) -> bool:
+    """Does autograd record this call?  (Decided outside Function.forward, where grad mode is
+    always off; under no_grad the kernel then skips the activation stash.)"""
+    return th.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
 def field_samples(model, pos, dir, pixel_width=None, t_start=None, t_end=None):
     n = pos.shape[0]
     dev = pos.device
@@ -57,7 +62,8 @@ def field_samples(model, pos, dir, pixel_width=None, t_start=None, t_end=None):
     pw = _prep(pixel_width, n, 1, dev)
     t0 = _prep(t_start, n, 1, dev)
     t1 = _prep(t_end, n, 1, dev)
-    return _FieldFunction.apply(model, "samples", 1, 0, pos, dir, t0, t1, pw, *model.fused_field().own_params)
+    params = model.fused_field().own_params
+    return _FieldFunction.apply(model, "samples", 1, 0, _tracking([pos, dir, *params]), pos, dir, t0, t1, pw, *params)
 
 
 def field_rays(model, ray_o, ray_d, t_start, t_end, pixel_width, integration_strategy: str):
@@ -66,7 +72,8 @@ def field_rays(model, ray_o, ray_d, t_start, t_end, pixel_width, integration_str
     dev = ray_o.device
     t_mode = {"left": 0, "middle": 1}[integration_strategy]
     pw = None if pixel_width is None else _prep(pixel_width, B, 1, dev)
-    sigma, rgb = _FieldFunction.apply(model, "rays", S, t_mode, ray_o.contiguous().float(),
-                                      ray_d.contiguous().float(), t_start.contiguous(),
-                                      t_end.contiguous(), pw, *model.fused_field().own_params)
+    params = model.fused_field().own_params
+    sigma, rgb = _FieldFunction.apply(model, "rays", S, t_mode, _tracking([ray_o, ray_d, *params]),
+                                      ray_o.contiguous().float(), ray_d.contiguous().float(),
+                                      t_start.contiguous(), t_end.contiguous(), pw, *params)
     return sigma.view(B, S), rgb.view(B, S, 3)
