@@ -193,8 +193,8 @@ mlp_bwd_kernel(const __grid_constant__ MlpBwdParams p) {
           uint32_t va[16], vb[16], packed[8];
           const uint32_t acc_q = acc + (uint32_t)(16 * cq);
           tmem_ld16(acc_q, va);
-          drain.acquire_ordered(sm.slab_drained, (1u << oc) - 1u, lane);   // stash copies of the slabs have drained
           auto finish = [&](int j) {
+            drain.acquire(sm.slab_drained, j, lane);   // the stash copy of the slab's previous contents has drained
             store_packed16(packed, sts0, sts1, j);
             signal_slab(sm.slab_ready, j, lane);
             if (will_stash) { drain.pending |= 1u << j; drain.last = j; }

@@ -216,16 +216,25 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdParams p) {
           const float* bias_q = bias + 16 * cq;
           const uint32_t acc_q = acc + (uint32_t)(16 * cq);
           tmem_ld16(acc_q, va);
-          // the slabs are about to be rewritten: their stash copies must have drained
-          drain.acquire_ordered(sm.slab_drained, (1u << oc) - 1u, lane);
+          // A slab may be rewritten once its stash copy has drained; checked slab by slab right before
+          // the stores: waiting up front for the newest copy (the last slab of the previous op) held
+          // every epilogue back by ~900 cycles.
+          NB_TRACE(399, threadIdx.x == 0 && oi == 3);
           uint32_t sign_bits[4];
           auto finish = [&](int j, uint32_t bits) {
+            const bool tr = (threadIdx.x == 0 || threadIdx.x == 480) && oi == 3;   // trace builds only
+            const int ts = 400 + (threadIdx.x == 0 ? 0 : 24) + 6 * j;
+            drain.acquire(sm.slab_drained, j, lane);
+            NB_TRACE(ts + 1, tr);
             store_packed16(packed, sts0, sts1, j);
             sign_bits[j] = bits;    // stored after the last slab has been published: a global store in
                                     // flight makes the proxy fence (MEMBAR.ALL.CTA) wait for its ack
+            NB_TRACE(ts + 2, tr);
             fence_proxy_async();
+            NB_TRACE(ts + 3, tr);
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.slab_ready[j]);
+            NB_TRACE(ts + 4, tr);
             if (will_stash) { drain.pending |= 1u << j; drain.last = j; }
           };
           auto run = [&](auto relu_tag) {
@@ -234,11 +243,13 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdParams p) {
             for (int j = 0; j < 4; j += 2) {
               if (j < oc) {
                 tmem_ld_wait16(va);
+                NB_TRACE(400 + (threadIdx.x == 0 ? 0 : 24) + 6 * j, (threadIdx.x == 0 || threadIdx.x == 480) && oi == 3);
                 if (j + 1 < oc) tmem_ld16(acc_q + (uint32_t)(64 * (j + 1)), vb);
                 finish(j, act_math16<kRelu>(va, bias_q + 64 * j, packed));
               }
               if (j + 1 < oc) {
                 tmem_ld_wait16(vb);
+                NB_TRACE(400 + (threadIdx.x == 0 ? 0 : 24) + 6 * (j + 1), (threadIdx.x == 0 || threadIdx.x == 480) && oi == 3);
                 if (j + 2 < oc) tmem_ld16(acc_q + (uint32_t)(64 * (j + 2)), va);
                 finish(j + 1, act_math16<kRelu>(vb, bias_q + 64 * (j + 1), packed));
               }

@@ -420,6 +420,23 @@ __device__ __forceinline__ void mma_issuer_loop(const NbProgram& prog, const Til
         tc::mbar_wait(&sm.full[stage], phase);
         NB_TRACE(256 + oi * 8 + c, elected && oi < 16 && c < 8);
         tc::tcgen05_fence_after();
+        if (n_blocks == 1) {
+          // the common shape (one N block): nothing but the two descriptor low words changes per MMA
+          const uint32_t tc0 = tcol[0], id0 = idesc[0], br0 = brow[0];
+          for (int sub = 0; sub < n_sub; ++sub) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (k < k16) {
+                const uint64_t adesc = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2u * k);
+                const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + br0 + 2u * k);
+                if (elected) tc::umma(tc0, adesc, bdesc, id0, acc_in[0] | (uint32_t)(k > 0));
+              }
+            }
+            acc_in[0] = 1u;
+            a_lo += (NB_SLAB_BYTES >> 4);
+            b_lo += sub_stride;
+          }
+        } else
         for (int sub = 0; sub < n_sub; ++sub) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -439,6 +456,7 @@ __device__ __forceinline__ void mma_issuer_loop(const NbProgram& prog, const Til
           b_lo += sub_stride;
         }
         if (elected) tc::umma_commit(&sm.empty[stage]);
+        NB_TRACE(448 + c, elected && oi == 4);
         if (++stage == (uint32_t)sm.n_stages) { stage = 0; phase ^= 1u; }
       }
       // consume the productions this op did not read, so that no barrier runs two phases ahead

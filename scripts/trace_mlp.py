@@ -40,5 +40,12 @@ for i in range(min(n_ops, 16)):
     ch = [(t[128 + i * 8 + k].item() - base, t[256 + i * 8 + k].item() - base) for k in range(min(prog.ops[i].n_chunks, 8))]
     print(f"{i:2d} | {a:7d} {b:7d} {c:7d} {dd:7d} | {b-a:6d} {c-b:6d} {dd-c:6d} | " + " ".join(f"({x},{y})" for x, y in ch))
 if which == "fwd":
-    e = [t[383 + k].item() - base for k in range(8)]
-    print("op 2 slab 1 (thread 0): start | tmem ld waited | math | drained | STS+STG | proxy fence | syncwarp | arrive:", e, [b - a for a, b in zip(e, e[1:])])
+    a3 = t[3 * 4 + 2].item() - base
+    print(f"op 3 epilogue, relative to its acc_full seen by thread 0 ({a3}); drain wait done at +{t[399].item() - base - a3}")
+    for name, off in (("thread 0 (warp 0)", 400), ("thread 480 (warp 15)", 424)):
+        for j in range(4):
+            e = [t[off + 6 * j + k].item() - base - a3 for k in range(5)]
+            print(f"  {name} slab {j}: tmem-ld done {e[0]:6d} | math +{e[1]-e[0]:4d} | STS +{e[2]-e[1]:4d} | proxy fence +{e[3]-e[2]:4d} | arrive +{e[4]-e[3]:4d} -> {e[4]:6d}")
+    print("  op 4 MMA warp, chunk MMAs issued + committed at:", [t[448 + c].item() - base - a3 for c in range(4)],
+          " op 4 chunks (slab_ready seen, weights seen):", [(t[128 + 32 + c].item() - base - a3, t[256 + 32 + c].item() - base - a3) for c in range(4)],
+          " op 4 acc_full seen:", t[4 * 4 + 2].item() - base - a3)
