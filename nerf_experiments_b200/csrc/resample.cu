@@ -442,11 +442,13 @@ resample_icdf_fast_kernel(const float* __restrict__ edges, const float* __restri
                           const float* __restrict__ u_ray, int B, int Sc, int Sf,
                           float* __restrict__ out_edges, int32_t* __restrict__ out_idx) {
   __shared__ float2 s_ec_all[kWarps][kFastSc + 1];      // (edge, cdf)
+  __shared__ float s_sc_all[kWarps][kFastSc];           // (e1 - e0) / (c1 - c0) per bin, NaN: empty bin
   __shared__ float s_s_all[kWarps][kFastSf];            // sample centres
   __shared__ int s_p_all[kWarps][kFastSf];              // bin of every sample (only if requested)
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   float2* s_ec = s_ec_all[warp];
+  float* s_sc = s_sc_all[warp];
   float* s_s = s_s_all[warp];
   int* s_p = s_p_all[warp];
   const int per = (Sf + 31) / 32;                       // consecutive samples per lane (<= 8)
@@ -456,9 +458,17 @@ resample_icdf_fast_kernel(const float* __restrict__ edges, const float* __restri
     for (int i = lane; i <= Sc; i += 32) s_ec[i] = make_float2(edges[base + i], cdf[base + i]);
     const float bias = (u_ray != nullptr) ? u_ray[ray] : 0.5f;
     __syncwarp();
+    // the interpolation slope depends on the bin only: one IEEE division per bin (two per lane)
+    // instead of one per sample (six per lane at 64 -> 192), same operands, same result
+    for (int i = lane; i < Sc; i += 32) {
+      const float2 a = s_ec[i], b = s_ec[i + 1];
+      const float dc = __fsub_rn(b.y, a.y);
+      s_sc[i] = dc < 1e-10f ? __int_as_float(0x7fc00000) : __fdiv_rn(__fsub_rn(b.x, a.x), dc);
+    }
     const float u_floor = s_ec[0].y, u_ceil = s_ec[Sc].y;
     const float u_step = __fdiv_rn(__fsub_rn(u_ceil, u_floor), (float)Sf);
     const int k0 = lane * per;
+    __syncwarp();
     int q = 0;   // first index in [0, Sc+1) with cdf > u (upper bound), non-decreasing in k
     if (k0 < Sf) {
       const float u = __fadd_rn(u_floor, __fmul_rn(__fadd_rn((float)k0, bias), u_step));
@@ -476,13 +486,12 @@ resample_icdf_fast_kernel(const float* __restrict__ edges, const float* __restri
         while (q <= Sc && s_ec[q].y <= u) ++q;
         int p = q - 1;
         p = p < 0 ? 0 : (p > Sc - 1 ? Sc - 1 : p);
-        const float2 a = s_ec[p], b = s_ec[p + 1];
-        const float dc = __fsub_rn(b.y, a.y);
+        const float2 a = s_ec[p];
+        const float scale = s_sc[p];
         float sv;
-        if (dc < 1e-10f) {
-          sv = __fmul_rn(__fadd_rn(a.x, b.x), 0.5f);
+        if (scale != scale) {     // NaN marks a bin without cdf mass
+          sv = __fmul_rn(__fadd_rn(a.x, s_ec[p + 1].x), 0.5f);
         } else {
-          const float scale = __fdiv_rn(__fsub_rn(b.x, a.x), dc);
           sv = __fadd_rn(__fmul_rn(__fsub_rn(u, a.y), scale), a.x);
         }
         s_s[k] = sv;
