@@ -27,6 +27,7 @@ struct ActParams {
   float* dx;
   float* dp0;
   float* dp1;
+  float* dsum;     // optional (F): column sums of dx = bias gradient of the Linear in front
   int rows_per_block;
 };
 
@@ -65,6 +66,7 @@ __global__ void __launch_bounds__(kActThreads) act_bwd_kernel(const ActParams p)
   const long long r0 = (long long)blockIdx.x * p.rows_per_block;
   const long long r1 = r0 + p.rows_per_block < p.N ? r0 + p.rows_per_block : p.N;
   float a0 = 0.f, a1 = 0.f;   // parameter-gradient partial sums of this column
+  float asum = 0.f;           // column sum of dx
   for (long long r = r0; r < r1; ++r) {
     const long long i = r * p.F + f;
     const float x = ld_stream(p.x + i);
@@ -101,11 +103,13 @@ __global__ void __launch_bounds__(kActThreads) act_bwd_kernel(const ActParams p)
       a1 += go * x * sn;                     // d/ds
     }
     st_stream(p.dx + i, dx);
+    asum += dx;
   }
   if (p.kind != NERFB200_ACT_SARF) a0 *= 2.f * p0;   // v = p0^2 + 1e-6
   if (r1 > r0) {
     atomicAdd(p.dp0 + f, a0);
     if (p.kind == NERFB200_ACT_GABOR && p.dp1) atomicAdd(p.dp1 + f, a1);
+    if (p.dsum) atomicAdd(p.dsum + f, asum);
   }
 }
 
@@ -145,14 +149,14 @@ extern "C" int nerfb200_act_fwd(int kind, const float* x, const float* p0, const
 
 extern "C" int nerfb200_act_bwd(int kind, const float* x, const float* p0, const float* p1,
                                 const float* g, long long N, int F, float* dx, float* dp0,
-                                float* dp1, void* stream) {
+                                float* dp1, float* dsum, void* stream) {
   NB_CHECK_ARG(kind >= NERFB200_ACT_GAUSS && kind <= NERFB200_ACT_GABOR, "act_bwd: unknown kind %d", kind);
   NB_CHECK_ARG(N >= 0 && F >= 1, "act_bwd: bad shape N=%lld F=%d", N, F);
   NB_CHECK_ARG(kind != NERFB200_ACT_GABOR || (p1 && dp1), "act_bwd: the Gabor activation needs p1 and dp1");
   if (N == 0) return NERFB200_OK;
   NB_CHECK_ARG(x && p0 && g && dx && dp0, "act_bwd: null pointer");
   ActParams p{};
-  p.kind = kind; p.x = x; p.p0 = p0; p.p1 = p1; p.g = g; p.N = N; p.F = F; p.dx = dx; p.dp0 = dp0; p.dp1 = dp1;
+  p.kind = kind; p.x = x; p.p0 = p0; p.p1 = p1; p.g = g; p.N = N; p.F = F; p.dx = dx; p.dp0 = dp0; p.dp1 = dp1; p.dsum = dsum;
   dim3 grid;
   launch_shape(N, F, grid, p.rows_per_block);
   act_bwd_kernel<<<grid, kActThreads, 0, (cudaStream_t)stream>>>(p);

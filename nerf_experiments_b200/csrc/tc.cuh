@@ -46,7 +46,10 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 // The suspend-time hint lets the hardware park the thread until the phase completes (or the
 // hint, in nanoseconds, expires) instead of returning after the short default limit: pollers
 // then cost no issue slots of the scheduler they share with the epilogue warps.
-constexpr uint32_t kTryWaitSuspendNs = 20000u;
+#ifndef NB_SUSPEND_NS
+#define NB_SUSPEND_NS 20000u
+#endif
+constexpr uint32_t kTryWaitSuspendNs = NB_SUSPEND_NS;
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(

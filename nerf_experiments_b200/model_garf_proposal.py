@@ -17,4 +17,4 @@ class ProposalNetwork(_GaussNetBase):
             self._create_linear(128, 1), nn.Softplus(threshold=8))
 
     def forward(self, pos: th.Tensor) -> th.Tensor:
-        return self.model(pos)
+        return self._run(self.model, pos)

@@ -3,15 +3,18 @@
 `model_density_1.{0..7}`, `model_density_2.{0..6}`, `model_color.{0..3}`), seeded initialisation,
 `parameters_linear()` / `parameters_gaussian()` and `forward(pos, dir) -> (rgb, density)`.
 
-Round-1 status: the Gaussian activations run in the CUDA kernels of csrc/activations.cu; the
-Linear layers are plain library GEMMs (cuBLAS through torch). The layers are up to 1024 wide,
-which does not fit the 256-column tile program of the fused kernel: fusing this
-network is the round-2 item. th.compile of the reference is dropped (no tracing compiler)."""
+Round-1 status: the Gaussian activations (forward, input / parameter / bias gradients) run in the
+CUDA kernels of csrc/activations.cu; the Linear layers are plain library GEMMs (cuBLAS through
+torch) on the tensor cores with TF32 operands — the precision class the reference trains at
+(`matmul_tf32 = False` on a network restores fp32 GEMMs). The layers are up to 1024 wide, which
+does not fit the 256-column tile program of the fused kernel: fusing this network
+is the round-2 item. th.compile of the reference is dropped (no tracing compiler)."""
 from typing import Iterator
 
 import torch as th
 import torch.nn as nn
 
+from . import _lib, ops
 from .gaussian import GaussAct
 
 
@@ -22,6 +25,26 @@ class _GaussNetBase(nn.Module):
         self.gaussian_init_max = gaussian_init_max
         self._parameters_linear: list = []
         self._parameters_gaussian: list = []
+        self.matmul_tf32 = True
+
+    def _run(self, seq: nn.Sequential, x: th.Tensor) -> th.Tensor:
+        """seq(x) with every Linear (+ GaussAct) pair as one fused-gradient op."""
+        mods = list(seq)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, nn.Linear) and x.is_cuda:
+                nxt = mods[i + 1] if i + 1 < len(mods) else None
+                if isinstance(nxt, GaussAct):
+                    x = ops.linear_activation(x, m.weight, m.bias, _lib.ACT_GAUSS, nxt.inv_standard_deviation,
+                                              None, self.matmul_tf32)
+                    i += 2
+                    continue
+                x = ops.linear_activation(x, m.weight, m.bias, -1, None, None, self.matmul_tf32)
+            else:
+                x = m(x)
+            i += 1
+        return x
 
     def _create_linear(self, features_in: int, features_out: int) -> nn.Linear:
         linear = nn.Linear(features_in, features_out)
@@ -61,8 +84,8 @@ class RadianceNetwork(_GaussNetBase):
             self._create_linear(256, 3), nn.Sigmoid())
 
     def forward(self, pos: th.Tensor, dir: th.Tensor):
-        z1 = self.model_density_1(pos)
-        z2 = self.model_density_2(th.cat((z1, pos), dim=1))
+        z1 = self._run(self.model_density_1, pos)
+        z2 = self._run(self.model_density_2, th.cat((z1, pos), dim=1))
         density = self.softplus(z2[:, 128] - 1)
-        rgb = self.model_color(th.cat((z1[:, :128] + z2[:, :128], dir), dim=1))
+        rgb = self._run(self.model_color, th.cat((z1[:, :128] + z2[:, :128], dir), dim=1))
         return rgb, density

@@ -266,12 +266,82 @@ class _Activation(th.autograd.Function):
         dp1 = None if p1c is None else th.zeros_like(p1c)
         with th.cuda.device(x2.device):
             check(lib().nerfb200_act_bwd(ctx.kind, _ptr(x2), _ptr(p0c), _ptr(p1c), _ptr(g2), x2.shape[0], F,
-                                         _ptr(dx), _ptr(dp0), _ptr(dp1), _stream()), "act_bwd")
+                                         _ptr(dx), _ptr(dp0), _ptr(dp1), None, _stream()), "act_bwd")
         return None, dx.view(ctx.shape), dp0, dp1
 
 
 def activation(kind: int, x: th.Tensor, p0: th.Tensor, p1: Optional[th.Tensor] = None) -> th.Tensor:
     return _Activation.apply(kind, x, p0, p1)
+
+
+class _tf32_matmul:
+    """GEMMs inside run on the tensor cores with TF32 operands and fp32 accumulation — the precision
+    the reference trains at (th.set_float32_matmul_precision("high"), barf/run_barf.py:101;
+    garf/main.py:93 goes further down to fp16 autocast)."""
+
+    def __init__(self, enabled: bool):
+        self.enabled = enabled
+
+    def __enter__(self):
+        self.prev = th.backends.cuda.matmul.allow_tf32
+        if self.enabled:
+            th.backends.cuda.matmul.allow_tf32 = True
+
+    def __exit__(self, *exc):
+        th.backends.cuda.matmul.allow_tf32 = self.prev
+
+
+class _LinearActivation(th.autograd.Function):
+    """y = act(x W^T + b; p0[, p1]) (kind < 0: no activation).  The GEMMs are library calls
+    (cuBLAS through torch, TF32 tensor cores when `tf32`); the activation, its input gradient,
+    the parameter gradients AND the bias gradient come from one pass of the activation kernels.
+    Round-1 shape of the GARF networks (their fused tile kernel is round 2)."""
+
+    @staticmethod
+    def forward(ctx, kind, tf32, x, weight, bias, p0, p1):
+        x2 = _f32(x.reshape(-1, x.shape[-1]), "x")
+        with _tf32_matmul(tf32):
+            z = th.addmm(bias, x2, weight.t())
+        F = z.shape[1]
+        if kind >= 0:
+            p0c = _f32(p0.reshape(-1), "p0", (F,))
+            p1c = None if p1 is None else _f32(p1.reshape(-1), "p1", (F,))
+            y = th.empty_like(z)
+            with th.cuda.device(z.device):
+                check(lib().nerfb200_act_fwd(kind, _ptr(z), _ptr(p0c), _ptr(p1c), z.shape[0], F, _ptr(y), _stream()),
+                      "act_fwd")
+            ctx.save_for_backward(x2, weight, z, p0c, p1c)
+        else:
+            y = z
+            ctx.save_for_backward(x2, weight, None, None, None)
+        ctx.kind, ctx.tf32, ctx.in_shape = kind, tf32, x.shape
+        return y.view(*x.shape[:-1], F)
+
+    @staticmethod
+    def backward(ctx, g):
+        x2, weight, z, p0c, p1c = ctx.saved_tensors
+        F = weight.shape[0]
+        g2 = _f32(g.reshape(-1, F), "g")
+        dp0 = dp1 = None
+        if ctx.kind >= 0:
+            dz = th.empty_like(z)
+            dp0 = th.zeros_like(p0c)
+            dp1 = None if p1c is None else th.zeros_like(p1c)
+            db = th.zeros(F, device=z.device, dtype=th.float32)
+            with th.cuda.device(z.device):
+                check(lib().nerfb200_act_bwd(ctx.kind, _ptr(z), _ptr(p0c), _ptr(p1c), _ptr(g2), z.shape[0], F,
+                                             _ptr(dz), _ptr(dp0), _ptr(dp1), _ptr(db), _stream()), "act_bwd")
+        else:
+            dz = g2
+            db = g2.sum(0) if ctx.needs_input_grad[4] else None
+        with _tf32_matmul(ctx.tf32):
+            dx = (dz @ weight).view(ctx.in_shape) if ctx.needs_input_grad[2] else None
+            dw = dz.t() @ x2 if ctx.needs_input_grad[3] else None
+        return None, None, dx, dw, db, dp0, dp1
+
+
+def linear_activation(x, weight, bias, kind: int = -1, p0=None, p1=None, tf32: bool = True):
+    return _LinearActivation.apply(kind, tf32, x, weight, bias, p0, p1)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -69,23 +69,27 @@ def _seeded_nets(cuda):
     return prop.to(cuda), rad.to(cuda)
 
 
-def test_garf_networks_match_reference(cuda):
+@pytest.mark.parametrize("tf32", [False, True])
+def test_garf_networks_match_reference(cuda, tf32):
+    """fp32 GEMMs: tight against the reference's fp32 outputs / gradients.  TF32 GEMMs (the default, the
+    reference's own matmul precision class): rgb within the north-star 1e-2, gradients to a few per cent."""
     g = _g()
     prop, rad = _seeded_nets(cuda)
-    th.backends.cuda.matmul.allow_tf32 = False
+    prop.matmul_tf32 = rad.matmul_tf32 = tf32
+    rtol, atol, grtol, gatol = (1e-4, 1e-5, 5e-3, 2e-5) if not tf32 else (2e-2, 1e-2, 6e-2, 5e-3)
     rgb, dens = rad(g["net_pos"].to(cuda), g["net_dir"].to(cuda))
-    assert th.allclose(rgb.cpu(), g["rad_rgb"], rtol=1e-4, atol=1e-5)
-    assert th.allclose(dens.cpu(), g["rad_density"], rtol=1e-4, atol=1e-5)
+    assert th.allclose(rgb.cpu(), g["rad_rgb"], rtol=rtol, atol=atol)
+    assert th.allclose(dens.cpu(), g["rad_density"], rtol=rtol, atol=atol)
     ((rgb * g["up_rgb"].to(cuda)).sum() + (dens * g["up_density"].to(cuda)).sum()).backward()
     for n, p in rad.named_parameters():
         ref = g["rad.grad." + n]
-        assert th.allclose(_thin(p.grad).cpu(), ref, rtol=5e-3, atol=2e-5 * float(ref.abs().max() + 1)), n
+        assert th.allclose(_thin(p.grad).cpu(), ref, rtol=grtol, atol=gatol * float(ref.abs().max() + 1)), n
     sp = prop(g["net_pos"].to(cuda))
-    assert th.allclose(sp.cpu(), g["prop_sigma"], rtol=1e-4, atol=1e-5)
+    assert th.allclose(sp.cpu(), g["prop_sigma"], rtol=rtol, atol=atol)
     (sp * g["up_prop"].to(cuda)).sum().backward()
     for n, p in prop.named_parameters():
         ref = g["prop.grad." + n]
-        assert th.allclose(_thin(p.grad).cpu(), ref, rtol=5e-3, atol=2e-5 * float(ref.abs().max() + 1)), n
+        assert th.allclose(_thin(p.grad).cpu(), ref, rtol=grtol, atol=gatol * float(ref.abs().max() + 1)), n
 
 
 @pytest.mark.parametrize("training", [True, False])
@@ -94,6 +98,7 @@ def test_garf_model_chain_matches_oracle(cuda, training):
     th.backends.cuda.matmul.allow_tf32 = False
     th.manual_seed(3)
     m = GarfModel(2.0, 7.0, 32, 48, 0.5, 1.5, 1.0, 1e-3, 1e-4, 100, 0.0, 1e-3, 1e-4, 100, 0.0).to(cuda)
+    m.proposal_network.matmul_tf32 = m.radiance_network.matmul_tf32 = False   # tight comparison: fp32 GEMMs
     m.train(training)
     B = 24
     gen = th.Generator().manual_seed(11)
