@@ -45,6 +45,8 @@ __device__ __forceinline__ float act_forward(int kind, float x, float p0, float 
   }
 }
 
+constexpr int kActUnroll = 8;   // rows in flight per thread: the kernels are bound by memory-level parallelism
+
 __global__ void __launch_bounds__(kActThreads) act_fwd_kernel(const ActParams p) {
   const int f = blockIdx.y * kActThreads + threadIdx.x;
   if (f >= p.F) return;
@@ -52,10 +54,54 @@ __global__ void __launch_bounds__(kActThreads) act_fwd_kernel(const ActParams p)
   const float p1 = p.p1 ? p.p1[f] : 0.f;
   const long long r0 = (long long)blockIdx.x * p.rows_per_block;
   const long long r1 = r0 + p.rows_per_block < p.N ? r0 + p.rows_per_block : p.N;
-  for (long long r = r0; r < r1; ++r) {
+  long long r = r0;
+  for (; r + kActUnroll <= r1; r += kActUnroll) {
+    float x[kActUnroll];
+#pragma unroll
+    for (int u = 0; u < kActUnroll; ++u) x[u] = ld_stream(p.x + (r + u) * p.F + f);
+#pragma unroll
+    for (int u = 0; u < kActUnroll; ++u) st_stream(p.y + (r + u) * p.F + f, act_forward(p.kind, x[u], p0, p1));
+  }
+  for (; r < r1; ++r) {
     const long long i = r * p.F + f;
     st_stream(p.y + i, act_forward(p.kind, ld_stream(p.x + i), p0, p1));
   }
+}
+
+// dx and the parameter-gradient terms of one element
+__device__ __forceinline__ float act_backward(int kind, float x, float g, float p0, float p1, float& a0, float& a1) {
+  float dx;
+  if (kind == NERFB200_ACT_GAUSS) {
+    const float v = p0 * p0 + 1e-6f;
+    const float x2 = x * x;
+    const float ge = g * expf(-x2 * v);
+    dx = -ge * 2.f * x * v;
+    a0 += -ge * x2;                       // d/dv, chained to p0 by the caller
+  } else if (kind == NERFB200_ACT_SARF) {
+    const float xa = fabsf(x) + 1e-4f;
+    const float u = xa * xa;
+    const float inv_f2 = 1.f / (p0 * p0);
+    const float D = u + inv_f2;
+    const float a = p0 / D;
+    float sn, cs;
+    sincosf(a, &sn, &cs);
+    const float e = expf(-u);
+    // y = cos(a) e^-u, a = f / D, D = u + f^-2, u = (|x| + eps)^2
+    const float dy_du = e * (sn * p0 / (D * D) - cs);
+    const float sgn = x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f);   // torch.abs backward: sign(0) = 0
+    dx = g * dy_du * 2.f * xa * sgn;
+    const float da_df = 1.f / D + 2.f * inv_f2 / (D * D);
+    a0 += g * (-sn * e * da_df);
+  } else {
+    const float v = p0 * p0 + 1e-6f;
+    float sn, cs;
+    sincosf(p1 * x, &sn, &cs);
+    const float go = -expf(-v * x * x) * g;
+    dx = go * (2.f * cs * v * x + p1 * sn);
+    a0 += go * x * x * cs;                 // d/dv
+    a1 += go * x * sn;                     // d/ds
+  }
+  return dx;
 }
 
 __global__ void __launch_bounds__(kActThreads) act_bwd_kernel(const ActParams p) {
@@ -67,41 +113,24 @@ __global__ void __launch_bounds__(kActThreads) act_bwd_kernel(const ActParams p)
   const long long r1 = r0 + p.rows_per_block < p.N ? r0 + p.rows_per_block : p.N;
   float a0 = 0.f, a1 = 0.f;   // parameter-gradient partial sums of this column
   float asum = 0.f;           // column sum of dx
-  for (long long r = r0; r < r1; ++r) {
-    const long long i = r * p.F + f;
-    const float x = ld_stream(p.x + i);
-    const float g = ld_stream(p.g + i);
-    float dx;
-    if (p.kind == NERFB200_ACT_GAUSS) {
-      const float v = p0 * p0 + 1e-6f;
-      const float x2 = x * x;
-      const float ge = g * expf(-x2 * v);
-      dx = -ge * 2.f * x * v;
-      a0 += -ge * x2;                       // d/dv, chained to p0 below
-    } else if (p.kind == NERFB200_ACT_SARF) {
-      const float xa = fabsf(x) + 1e-4f;
-      const float u = xa * xa;
-      const float inv_f2 = 1.f / (p0 * p0);
-      const float D = u + inv_f2;
-      const float a = p0 / D;
-      float sn, cs;
-      sincosf(a, &sn, &cs);
-      const float e = expf(-u);
-      // y = cos(a) e^-u, a = f / D, D = u + f^-2, u = (|x| + eps)^2
-      const float dy_du = e * (sn * p0 / (D * D) - cs);
-      const float sgn = x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f);   // torch.abs backward: sign(0) = 0
-      dx = g * dy_du * 2.f * xa * sgn;
-      const float da_df = 1.f / D + 2.f * inv_f2 / (D * D);
-      a0 += g * (-sn * e * da_df);
-    } else {
-      const float v = p0 * p0 + 1e-6f;
-      float sn, cs;
-      sincosf(p1 * x, &sn, &cs);
-      const float go = -expf(-v * x * x) * g;
-      dx = go * (2.f * cs * v * x + p1 * sn);
-      a0 += go * x * x * cs;                 // d/dv
-      a1 += go * x * sn;                     // d/ds
+  long long r = r0;
+  for (; r + kActUnroll <= r1; r += kActUnroll) {
+    float x[kActUnroll], g[kActUnroll];
+#pragma unroll
+    for (int u = 0; u < kActUnroll; ++u) {
+      x[u] = ld_stream(p.x + (r + u) * p.F + f);
+      g[u] = ld_stream(p.g + (r + u) * p.F + f);
     }
+#pragma unroll
+    for (int u = 0; u < kActUnroll; ++u) {   // same summation order as the row-by-row loop
+      const float dx = act_backward(p.kind, x[u], g[u], p0, p1, a0, a1);
+      st_stream(p.dx + (r + u) * p.F + f, dx);
+      asum += dx;
+    }
+  }
+  for (; r < r1; ++r) {
+    const long long i = r * p.F + f;
+    const float dx = act_backward(p.kind, ld_stream(p.x + i), ld_stream(p.g + i), p0, p1, a0, a1);
     st_stream(p.dx + i, dx);
     asum += dx;
   }
