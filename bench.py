@@ -220,10 +220,12 @@ def run_ours(args):
         v["gbs"] = alg_bytes[k] / (v["ms"] * 1e-3) / 1e9
         v["bytes_per_launch"] = alg_bytes[k]
     # DRAM traffic of the same kernel per launch, from the committed `ncu --set full` capture of
-    # this workload (profiles/r1_traffic.json; dram__bytes_read.sum + dram__bytes_write.sum)
+    # this workload (newest profiles/r*_traffic.json; dram__bytes_read.sum + dram__bytes_write.sum)
     traffic = None
     try:
-        prof = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")))
+        import glob
+        newest = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r*_traffic.json")))[-1]
+        prof = json.load(open(newest))
         kname = {"mlp_fwd_train": "mlp_fwd_kernel", "mlp_bwd_inputs": "mlp_bwd_kernel", "mlp_bwd": "mlp_bwd_kernel",
                  "mlp_wgrad": "mlp_wgrad_kernel"}[top]
         rec = prof["kernels"][kname]
