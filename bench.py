@@ -173,15 +173,24 @@ def run_ours(args):
     ms_total = float(t_ms.item())
 
     # ---- end-to-end: host buffers in, loss out, every step ------------------------------------
+    # through the public host-batch API (engine.HostStepper): every step copies its inputs from
+    # pinned host memory (on a copy stream, overlapping the previous step) and copies its loss
+    # back; the host reads each loss one step late so that it never waits on the step in flight.
+    from nerf_experiments_b200.engine import HostStepper
+    stepper = HostStepper(eng)
     barrier()
     e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
     e0.record()
-    last = 0.0
+    losses = []
     for i in range(K):
-        dev_batch = tuple(t.to(dev, non_blocking=True) for t in host_batches[i])
-        last = float(eng.step(*dev_batch).item())                 # D2H read of the step's loss
+        prev = stepper.submit(host_batches[i])
+        if prev is not None:
+            losses.append(prev)
+    losses.append(stepper.flush())                                  # D2H read of the last step's loss
     e1.record()
     barrier()
+    last = losses[-1]
+    assert len(losses) == K
     t_e2e = th.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)

@@ -104,3 +104,58 @@ class TrainEngine:
         loss.backward()
         self.optimizer_step()
         return loss_fine.detach()
+
+
+class HostStepper:
+    """Training from HOST batches without stalling the device: the host->device copy of batch
+    i + 1 runs on a copy stream while step i computes, and the loss of every step is copied to
+    pinned memory asynchronously and handed back one call later, so the host never waits for the
+    step it has just enqueued (the reference's loop copies, computes and reads the loss back to
+    back, barf/model_interpolation.py:490-526, 588-597).
+
+        stepper = HostStepper(engine)
+        for batch in pinned_host_batches:        # tuples (o, d, target, img_idx, pixel_width)
+            loss_of_previous_step = stepper.submit(batch)   # None for the first call
+        last_loss = stepper.flush()
+    """
+
+    def __init__(self, engine: TrainEngine, coarse_weight: float = 1.0):
+        self.engine = engine
+        self.coarse_weight = coarse_weight
+        self.copy_stream = th.cuda.Stream(device=engine.device)
+        self.staging = [None, None]
+        self.ready = [th.cuda.Event(), th.cuda.Event()]       # H2D of the slot has landed
+        self.done = [None, None]                              # the step that used the slot has finished
+        self.loss_host = [th.zeros(1).pin_memory(), th.zeros(1).pin_memory()]
+        self.count = 0
+        self.h2d_bytes = 0
+
+    def _read(self, slot: int) -> float:
+        self.done[slot].synchronize()
+        return float(self.loss_host[slot][0])
+
+    def submit(self, host_batch):
+        s = self.count & 1
+        compute = th.cuda.current_stream(self.engine.device)
+        with th.cuda.stream(self.copy_stream):
+            if self.done[s] is not None:
+                self.copy_stream.wait_event(self.done[s])     # the slot's previous step has consumed it
+            if self.staging[s] is None:
+                self.staging[s] = tuple(th.empty(t.shape, dtype=t.dtype, device=self.engine.device) for t in host_batch)
+            for dst, src in zip(self.staging[s], host_batch):
+                dst.copy_(src, non_blocking=True)
+            self.ready[s].record(self.copy_stream)
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in host_batch)
+        compute.wait_event(self.ready[s])
+        loss = self.engine.step(*self.staging[s], coarse_weight=self.coarse_weight)
+        self.loss_host[s].copy_(loss.reshape(1), non_blocking=True)
+        ev = th.cuda.Event()
+        ev.record(compute)
+        self.done[s] = ev
+        self.count += 1
+        # read the PREVIOUS step's loss only now: this step is already queued behind it, so the
+        # device does not idle while the host waits
+        return self._read(s ^ 1) if self.count > 1 else None
+
+    def flush(self):
+        return self._read((self.count - 1) & 1) if self.count > 0 else None

@@ -126,3 +126,32 @@ def test_engine_matches_torch_adam(cuda):
     for k in finals["torch"]:
         a, b = finals["engine"][k], finals["torch"][k]
         assert (a - b).abs().max() <= 2e-4 * max(1.0, b.abs().max().item()) + 2e-4, k
+
+
+def test_host_stepper_matches_direct_steps(cuda):
+    """HostStepper (copy stream + deferred loss read-back) gives the losses and parameters of plain
+    engine.step calls on the same batches, one call late."""
+    from nerf_experiments_b200.engine import HostStepper, TrainEngine
+    B = 96
+    batches = [_rays(B, 5, 30 + s) for s in range(5)]
+    results = {}
+    for mode in ("direct", "host"):
+        model, cam = _build(cuda, True, 0, 32, seed=9)
+        eng = TrainEngine(model, cuda)
+        th.manual_seed(5)
+        if mode == "direct":
+            ls = [eng.step(*(t.to(cuda) for t in (o, d, target, idx, pw))).item() for (o, d, target, idx, pw) in batches]
+        else:
+            st = HostStepper(eng)
+            ls = []
+            for (o, d, target, idx, pw) in batches:
+                prev = st.submit(tuple(t.pin_memory() for t in (o, d, target, idx, pw)))
+                if prev is not None:
+                    ls.append(prev)
+            ls.append(st.flush())
+            assert st.h2d_bytes == sum(t.numel() * t.element_size() for t in batches[0])
+        results[mode] = (ls, eng.flat.flat.detach().clone())
+    assert len(results["host"][0]) == 5
+    assert results["direct"][0] == pytest.approx(results["host"][0], rel=1e-6)
+    # gradients are flushed with floating-point atomics: equal up to summation order
+    assert th.allclose(results["direct"][1], results["host"][1], rtol=0, atol=2e-5)
