@@ -272,7 +272,7 @@ def run_ours(args):
         "gpu_launches": int(launches), "loss": float(loss.item()), "loss_e2e": last,
         "clocks": clocks.summary(), "roofline": roofline, "cpu_baseline": cpu,
     }
-    print(json.dumps(out))
+    emit_json(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -348,7 +348,29 @@ def run_reference(args):
                       "host cores; each step is a bounded sample of the workload"},
            "cpu_baseline": cpu,
            "e2e": {"value": cpu["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    emit_json(out)
+
+
+_STDOUT_FD = None
+
+
+def capture_stdout():
+    """stdout carries the one JSON line and nothing else: whatever libraries print there (NCCL's
+    version banner under NCCL_DEBUG, for one) is diverted to stderr at file-descriptor level."""
+    global _STDOUT_FD
+    if _STDOUT_FD is None:
+        sys.stdout.flush()
+        _STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    if _STDOUT_FD is None:
+        os.write(1, line)
+    else:
+        os.write(_STDOUT_FD, line)
 
 
 def main():
@@ -369,6 +391,7 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__),
                "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup), "--impl", args.impl]
         sys.exit(subprocess.call(cmd))
+    capture_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
