@@ -142,7 +142,6 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdParams p) {
       }
       return out;
     };
-    uint16_t* const masks16 = reinterpret_cast<uint16_t*>(p.masks);
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long n_raw = (long long)tile * NB_TILE_ROWS + row;
       const bool valid = n_raw < p.N;
@@ -174,7 +173,6 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdParams p) {
       for (int oi = 0; oi < p.prog.n_ops; ++oi) {
         const NbOp& op = p.prog.ops[oi];
         const float* bias = sm.floats + op.bias_off;
-        const bool stores_act = fwd_stores_act(op.epi);
         const uint32_t buf = g_op & 1u;
         const uint32_t acc = tmem_lane + buf * kAccCols;
         if (oi == sched.reencode_op) {
@@ -190,13 +188,19 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdParams p) {
           signal_slabs(sm.slab_ready, sched.reencode_mask, lane);
           if (training && p.pe_dir.stash_slab >= 0) drain.produced(sched.reencode_mask);
         }
+        // Everything the epilogue needs from the program (constant-bank loads with a dynamic
+        // index, ~100 cycles each and dependent) is fetched and pinned in registers BEFORE the
+        // wait for the accumulator, so that the first TMEM load issues right after it.
+        int epi_r = op.epi, oc_r = op.out_chunks, mask_word_r = op.mask_word, stash_slab_r = op.stash_slab;
+        uint32_t* mask_base = p.masks + (((size_t)tile * p.prog.mask_words_per_tile + (mask_word_r < 0 ? 0 : mask_word_r) + (cq >> 1)) * NB_TILE_ROWS + row);
+        asm volatile("" : "+r"(epi_r), "+r"(oc_r), "+r"(mask_word_r), "+r"(stash_slab_r), "+l"(mask_base));
         warp_mbar_wait(&sm.acc_full[buf], (g_op >> 1) & 1u, lane);
         tcgen05_fence_after();
         NB_TRACE(oi * 4 + 2, threadIdx.x == 0);
-        if (stores_act) {
-          const bool relu = (op.epi == NB_EPI_RELU || op.epi == NB_EPI_RELU_SIGMA);
-          const int oc = op.out_chunks;
-          if ((op.epi == NB_EPI_LINEAR_SIGMA || op.epi == NB_EPI_RELU_SIGMA) && cq == 3) {
+        if (fwd_stores_act(epi_r)) {
+          const bool relu = (epi_r == NB_EPI_RELU || epi_r == NB_EPI_RELU_SIGMA);
+          const int oc = oc_r;
+          if ((epi_r == NB_EPI_LINEAR_SIGMA || epi_r == NB_EPI_RELU_SIGMA) && cq == 3) {
             // the density column sits in the first columns of the other buffer: it must be read
             // before slab 0 is published (the next op's MMAs reuse that buffer from then on)
             uint32_t e[16];
@@ -207,10 +211,9 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdParams p) {
             if (valid) p.out_sigma[n] = softplus8(pre + p.sigma_bias);
           }
           // sign bits: one 32-bit word per (row, 32-column group), this thread owns half of it
-          uint16_t* mask_out = (training && relu && op.mask_word >= 0)
-              ? masks16 + (((size_t)tile * p.prog.mask_words_per_tile + op.mask_word + (cq >> 1)) * NB_TILE_ROWS + row) * 2 + (cq & 1)
-              : nullptr;
-          const uint32_t will_stash = (training && op.stash_slab >= 0) ? 1u : 0u;
+          uint16_t* mask_out = (training && relu && mask_word_r >= 0)
+              ? reinterpret_cast<uint16_t*>(mask_base) + (cq & 1) : nullptr;
+          const uint32_t will_stash = (training && stash_slab_r >= 0) ? 1u : 0u;
           // the TMEM load of slab j+1 is in flight during the math of slab j
           uint32_t va[16], vb[16], packed[8];
           const float* bias_q = bias + 16 * cq;
@@ -270,7 +273,7 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdParams p) {
             p.out_rgb[n * 3 + 0] = sigmoidf(__uint_as_float(v[0]) + bias[0]);
             p.out_rgb[n * 3 + 1] = sigmoidf(__uint_as_float(v[1]) + bias[1]);
             p.out_rgb[n * 3 + 2] = sigmoidf(__uint_as_float(v[2]) + bias[2]);
-            if (op.epi == NB_EPI_RGB_SIGMA)
+            if (epi_r == NB_EPI_RGB_SIGMA)
               p.out_sigma[n] = softplus8(__uint_as_float(v[3]) + bias[3] + p.sigma_bias);
           }
         }

@@ -152,6 +152,6 @@ def test_host_stepper_matches_direct_steps(cuda):
             assert st.h2d_bytes == sum(t.numel() * t.element_size() for t in batches[0])
         results[mode] = (ls, eng.flat.flat.detach().clone())
     assert len(results["host"][0]) == 5
-    assert results["direct"][0] == pytest.approx(results["host"][0], rel=1e-6)
+    assert results["direct"][0] == pytest.approx(results["host"][0], rel=1e-4)   # atomics: summation order varies
     # gradients are flushed with floating-point atomics: equal up to summation order
     assert th.allclose(results["direct"][1], results["host"][1], rtol=0, atol=2e-5)
