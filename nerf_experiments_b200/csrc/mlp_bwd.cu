@@ -194,7 +194,6 @@ mlp_bwd_kernel(const __grid_constant__ MlpBwdParams p) {
           const uint32_t acc_q = acc + (uint32_t)(16 * cq);
           tmem_ld16(acc_q, va);
           auto finish = [&](int j) {
-            drain.acquire(sm.slab_drained, j, lane);   // the stash copy of the slab's previous contents has drained
             store_packed16(packed, sts0, sts1, j);
             signal_slab(sm.slab_ready, j, lane);
             if (will_stash) { drain.pending |= 1u << j; drain.last = j; }
@@ -202,12 +201,14 @@ mlp_bwd_kernel(const __grid_constant__ MlpBwdParams p) {
 #pragma unroll
           for (int j = 0; j < 4; j += 2) {
             if (j < oc) {
-              tmem_ld_wait16(va);
+              drain.acquire(sm.slab_drained, j, lane);   // the stash copy of the slab's previous contents has
+              tmem_ld_wait16(va);                        // drained (checked while the TMEM load is in flight)
               if (j + 1 < oc) tmem_ld16(acc_q + (uint32_t)(64 * (j + 1)), vb);
               grad_math16(va, mbits[j], packed);
               finish(j);
             }
             if (j + 1 < oc) {
+              drain.acquire(sm.slab_drained, j + 1, lane);
               tmem_ld_wait16(vb);
               if (j + 2 < oc) tmem_ld16(acc_q + (uint32_t)(64 * (j + 2)), va);
               grad_math16(vb, mbits[j + 1], packed);

@@ -42,18 +42,14 @@ struct FwdStashDst {
 // bound by the number of instructions the four row warps of a scheduler issue per slab, so
 // ReLU rides in the convert (cvt.rn.relu.bf16x2.f32) and each sign bit costs one funnel shift.
 template <bool kRelu>
-__device__ __forceinline__ uint32_t act_math16(const uint32_t (&v)[16], const float* bias16,
+__device__ __forceinline__ uint32_t act_math16(const uint32_t (&v)[16], const float4 (&bias16)[4],
                                                uint32_t (&packed)[8]) {
   // two independent sign chains (one long funnel-shift chain is latency bound): chain c collects
   // elements 8c..8c+7, the first element ends up in the highest of its 8 bits
   uint32_t neg[2] = {0u, 0u};
 #pragma unroll
   for (int i = 0; i < 16; i += 4) {
-#ifdef NB_EXP_NOBIAS
-    const float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
-#else
-    const float4 bq = *reinterpret_cast<const float4*>(bias16 + i);
-#endif
+    const float4 bq = bias16[i >> 2];
     const float a0 = __uint_as_float(v[i]) + bq.x, a1 = __uint_as_float(v[i + 1]) + bq.y;
     const float a2 = __uint_as_float(v[i + 2]) + bq.z, a3 = __uint_as_float(v[i + 3]) + bq.w;
     if (kRelu) {
@@ -219,15 +215,14 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdParams p) {
           const float* bias_q = bias + 16 * cq;
           const uint32_t acc_q = acc + (uint32_t)(16 * cq);
           tmem_ld16(acc_q, va);
-          // A slab may be rewritten once its stash copy has drained; checked slab by slab right before
-          // the stores: waiting up front for the newest copy (the last slab of the previous op) held
+          // A slab may be rewritten once its stash copy has drained; checked slab by slab (while the
+          // slab's TMEM load is in flight): waiting up front for the newest copy (the last slab of the previous op) held
           // every epilogue back by ~900 cycles.
           NB_TRACE(399, threadIdx.x == 0 && oi == 3);
           uint32_t sign_bits[4];
           auto finish = [&](int j, uint32_t bits) {
             const bool tr = (threadIdx.x == 0 || threadIdx.x == 480) && oi == 3;   // trace builds only
             const int ts = 400 + (threadIdx.x == 0 ? 0 : 24) + 6 * j;
-            drain.acquire(sm.slab_drained, j, lane);
             NB_TRACE(ts + 1, tr);
             store_packed16(packed, sts0, sts1, j);
             sign_bits[j] = bits;    // stored after the last slab has been published: a global store in
@@ -240,21 +235,30 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdParams p) {
             NB_TRACE(ts + 4, tr);
             if (will_stash) { drain.pending |= 1u << j; drain.last = j; }
           };
+          float4 bq[4];
+          auto load_bias = [&](const float* b16) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) bq[i] = *reinterpret_cast<const float4*>(b16 + 4 * i);
+          };
           auto run = [&](auto relu_tag) {
             constexpr bool kRelu = decltype(relu_tag)::value;
 #pragma unroll
             for (int j = 0; j < 4; j += 2) {
               if (j < oc) {
+                drain.acquire(sm.slab_drained, j, lane);       // both overlap the TMEM load in flight
+                load_bias(bias_q + 64 * j);
                 tmem_ld_wait16(va);
                 NB_TRACE(400 + (threadIdx.x == 0 ? 0 : 24) + 6 * j, (threadIdx.x == 0 || threadIdx.x == 480) && oi == 3);
                 if (j + 1 < oc) tmem_ld16(acc_q + (uint32_t)(64 * (j + 1)), vb);
-                finish(j, act_math16<kRelu>(va, bias_q + 64 * j, packed));
+                finish(j, act_math16<kRelu>(va, bq, packed));
               }
               if (j + 1 < oc) {
+                drain.acquire(sm.slab_drained, j + 1, lane);
+                load_bias(bias_q + 64 * (j + 1));
                 tmem_ld_wait16(vb);
                 NB_TRACE(400 + (threadIdx.x == 0 ? 0 : 24) + 6 * (j + 1), (threadIdx.x == 0 || threadIdx.x == 480) && oi == 3);
                 if (j + 2 < oc) tmem_ld16(acc_q + (uint32_t)(64 * (j + 2)), va);
-                finish(j + 1, act_math16<kRelu>(vb, bias_q + 64 * (j + 1), packed));
+                finish(j + 1, act_math16<kRelu>(vb, bq, packed));
               }
             }
           };

@@ -153,5 +153,7 @@ def test_host_stepper_matches_direct_steps(cuda):
         results[mode] = (ls, eng.flat.flat.detach().clone())
     assert len(results["host"][0]) == 5
     assert results["direct"][0] == pytest.approx(results["host"][0], rel=1e-4)   # atomics: summation order varies
-    # gradients are flushed with floating-point atomics: equal up to summation order
-    assert th.allclose(results["direct"][1], results["host"][1], rtol=0, atol=2e-5)
+    # gradients are flushed with floating-point atomics: equal up to summation order, which Adam's
+    # normalisation can blow up to a full lr-sized step for the odd parameter with a near-zero gradient
+    diff = (results["direct"][1] - results["host"][1]).abs()
+    assert float((diff > 2e-5).float().mean()) < 1e-3 and float(diff.max()) < 5 * 1e-3
