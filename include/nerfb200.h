@@ -180,6 +180,17 @@ int nerfb200_mlp_fwd(const void* program_host, const void* wpack, const float* b
                      const NbPeCfg* pe_dir_host, const float* alpha_pos,
                      const float* alpha_dir, float sigma_bias, float* out_sigma, float* out_rgb,
                      void* stash, uint32_t* masks, int n_bias_floats, void* stream);
+/* The same forward with two 128-sample tiles in flight per CTA (the epilogue of one runs under the
+ * MMAs of the other). Takes the forward weights packed as per-K-step images (NbPackChunk.img_rows
+ * > 0) and the float offset of the density weight row inside the packed biases (-1: the network
+ * has no "extra" density column). Programs it cannot run (6-slab shape, density row riding in a
+ * main image) are rejected with NERFB200_ERR_ARG: use nerfb200_mlp_fwd. Same stash / mask layout. */
+int nerfb200_mlp_fwd2(const void* program, const void* wpack_k16, const float* bias,
+                      const NbMlpInputs* in, const NbPeCfg* pe_pos, const NbPeCfg* pe_dir,
+                      const float* alpha_pos, const float* alpha_dir, float sigma_bias,
+                      float* out_sigma, float* out_rgb, void* stash, uint32_t* masks,
+                      int n_bias_floats, int density_w_off, void* stream);
+
 int nerfb200_mlp_bwd(const void* program_host, const void* wpack_t,
                      const NbMlpInputs* in_host, const NbPeCfg* pe_pos_host,
                      const NbPeCfg* pe_dir_host, const float* alpha_pos,

@@ -141,6 +141,11 @@ typedef struct {
   int32_t dst_off;              /* 1024 B units into the packed buffer                        */
   int32_t dst_row0;             /* first image row written                                    */
   int32_t dst_row_step;         /* image-row step (>= 1)                                      */
+  int32_t img_rows;             /* 0: one [rows][64] image in the 128B-swizzled slab layout;  */
+                                /* > 0: four [img_rows][16] images (one per 16-column K step, */
+                                /* img_rows * 32 B apart) in the 32B-swizzled K-major layout  */
+                                /* the two-tile forward kernel streams one MMA at a time      */
+  int32_t reserved;
 } NbPackChunk;
 
 /* A packed bias segment: dst[dst_off + i] = params[base + i] for i < n, 0 for n <= i < n_padded */

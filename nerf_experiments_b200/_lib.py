@@ -69,11 +69,14 @@ class NbMlpInputs(C.Structure):
 class NbPackChunk(C.Structure):
     _fields_ = [("base", C.c_int64), ("row_stride", C.c_int32), ("col_stride", C.c_int32),
                 ("n_rows", C.c_int32), ("n_cols", C.c_int32), ("rows_padded", C.c_int32),
-                ("dst_off", C.c_int32), ("dst_row0", C.c_int32), ("dst_row_step", C.c_int32)]
+                ("dst_off", C.c_int32), ("dst_row0", C.c_int32), ("dst_row_step", C.c_int32),
+                ("img_rows", C.c_int32), ("reserved", C.c_int32)]
 
     def __init__(self, *args, **kw):
         kw.setdefault("dst_row0", 0)
         kw.setdefault("dst_row_step", 1)
+        kw.setdefault("img_rows", 0)
+        kw.setdefault("reserved", 0)
         super().__init__(*args, **kw)
 
 
@@ -131,6 +134,8 @@ def _declare(L):
     L.nerfb200_mlp_pack.argtypes = [vp, vp, i32, vp, vp, i32, vp, vp]
     L.nerfb200_mlp_fwd.argtypes = [vp, vp, vp, C.POINTER(NbMlpInputs), C.POINTER(NbPeCfg),
                                    C.POINTER(NbPeCfg), vp, vp, f32, vp, vp, vp, vp, i32, vp]
+    L.nerfb200_mlp_fwd2.argtypes = [vp, vp, vp, C.POINTER(NbMlpInputs), C.POINTER(NbPeCfg),
+                                    C.POINTER(NbPeCfg), vp, vp, f32, vp, vp, vp, vp, i32, i32, vp]
     L.nerfb200_mlp_bwd.argtypes = [vp, vp, C.POINTER(NbMlpInputs), C.POINTER(NbPeCfg), C.POINTER(NbPeCfg),
                                    vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, i32, i32, vp, vp, vp, vp, vp]
     L.nerfb200_mlp_wgrad.argtypes = [vp, i32, vp, i32, vp, i32, vp, vp]
@@ -155,7 +160,7 @@ EXPORTS = [
     "nerfb200_sample_uniform", "nerfb200_composite_fwd", "nerfb200_composite_bwd",
     "nerfb200_resample_alloc", "nerfb200_resample_fallback", "nerfb200_resample_icdf",
     "nerfb200_pose_fwd", "nerfb200_pose_bwd", "nerfb200_so3_to_SO3",
-    "nerfb200_mlp_pack", "nerfb200_mlp_fwd", "nerfb200_mlp_bwd", "nerfb200_mlp_wgrad", "nerfb200_pe_fwd", "nerfb200_pe_bwd",
+    "nerfb200_mlp_pack", "nerfb200_mlp_fwd", "nerfb200_mlp_fwd2", "nerfb200_mlp_bwd", "nerfb200_mlp_wgrad", "nerfb200_pe_fwd", "nerfb200_pe_bwd",
     "nerfb200_adam_step", "nerfb200_act_fwd", "nerfb200_act_bwd", "nerfb200_ray_batch", "nerfb200_kabsch",
 ]
 

@@ -304,6 +304,19 @@ __device__ __forceinline__ void load_sample(const NbMlpInputs& in, long long n, 
   }
 }
 
+// Writes the encoding of one sample as bf16 into row `row` of a slab (zero padded).
+__device__ __forceinline__ void encode_to_slab_at(const NbPeCfg& cfg, const float* mask,
+                                                  const PeSample& s, uint8_t* slab, int row) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    *reinterpret_cast<uint4*>(slab + (uint32_t)row * 128u + ((uint32_t)(q ^ (row & 7)) << 4)) =
+        make_uint4(0u, 0u, 0u, 0u);
+  pe_encode(cfg, mask, s, [&](int col, float v) {
+    *reinterpret_cast<__nv_bfloat16*>(slab + tc::slab_offset((uint32_t)row, (uint32_t)col)) =
+        __float2bfloat16_rn(v);
+  });
+}
+
 // Writes the encoding of one sample as bf16 into row `row` of the encoder's slab (zero padded).
 __device__ __forceinline__ void encode_to_slab(const NbPeCfg& cfg, const float* mask,
                                                const PeSample& s, const MlpSmem& sm, int row) {

@@ -34,8 +34,16 @@ mlp_pack_kernel(const float* __restrict__ params, const NbPackChunk* __restrict_
         w[h] = tc::pack_bf16(v[0], v[1]);
       }
       const int R = ch.dst_row0 + r * ch.dst_row_step;   // image row
-      *reinterpret_cast<uint4*>(dst + (size_t)R * 128u + ((uint32_t)(q ^ (R & 7)) << 4)) =
-          make_uint4(w[0], w[1], w[2], w[3]);
+      if (ch.img_rows > 0) {
+        // one [img_rows][16] image per K step, rows of 32 B, 16-byte halves swizzled with row bit 2
+        // (canonical UMMA SWIZZLE_32B K-major layout)
+        const uint32_t off = (uint32_t)(q >> 1) * (uint32_t)ch.img_rows * 32u + (uint32_t)R * 32u +
+                             ((uint32_t)((q & 1) ^ ((R >> 2) & 1)) << 4);
+        *reinterpret_cast<uint4*>(dst + off) = make_uint4(w[0], w[1], w[2], w[3]);
+      } else {
+        *reinterpret_cast<uint4*>(dst + (size_t)R * 128u + ((uint32_t)(q ^ (R & 7)) << 4)) =
+            make_uint4(w[0], w[1], w[2], w[3]);
+      }
     }
   } else if (d - n_chunks < n_biases) {
     const NbPackBias b = biases[d - n_chunks];

@@ -202,6 +202,18 @@ __device__ __forceinline__ uint64_t umma_desc_mnmajor(uint32_t slab_addr, uint32
   return umma_desc(slab_addr + k16 * 2048u, slab_stride, 1024u);
 }
 
+// K-major operand in the SWIZZLE_32B layout: rows of 16 bf16 (32 B), 8-row groups 256 B apart, the
+// two 16-byte halves of a row swapped when row bit 2 is set; one [rows][16] image = one K step.
+__device__ __forceinline__ uint64_t umma_desc_kmajor_sw32(uint32_t image_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((image_addr >> 4) & 0x3FFFu);
+  d |= (uint64_t)1 << 16;                       // LBO (unused for swizzled K-major layouts)
+  d |= (uint64_t)((256u >> 4) & 0x3FFFu) << 32; // SBO
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;                       // SWIZZLE_32B
+  return d;
+}
+
 // Instruction descriptor, kind::f16, bf16 x bf16 -> fp32 (cute::UMMA::InstrDescriptor bits).
 __device__ __host__ constexpr uint32_t umma_idesc(int M, int N, bool a_mn_major, bool b_mn_major) {
   return (1u << 4)                         // c_format = F32

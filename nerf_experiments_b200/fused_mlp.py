@@ -87,6 +87,11 @@ class FusedField:
         # optional per-kernel timing (bench.py): name -> list of (start, end) CUDA events
         # recorded on the launching stream; None = off
         self.timers = None
+        # Experimental: two 128-sample tiles in flight per CTA (csrc/mlp_fwd.cu, mlp_fwd2) when the
+        # program qualifies. Opt-in: measured on B200 it ties the one-tile kernel without the stash
+        # (1.00 ms) and loses with it (1.40 vs 1.08 ms) — see DESIGN.md section 4.
+        import os
+        self.use_two_tile = os.environ.get("NERFB200_TWO_TILE", "0") == "1"
 
     # -- compilation / packing ------------------------------------------------------------
     def prepare(self, device):
@@ -112,6 +117,14 @@ class FusedField:
                 units += cb.wpack_units
                 all_chunks += cb.pack_chunks
                 self.bwd[want] = cb
+            # the forward weights once more as per-K-step images for the two-tile forward kernel
+            self.k16_units = -1
+            if cm.two_tile_ok:
+                self.k16_units = units
+                for ch in cm.pack_chunks_k16:
+                    ch.dst_off += units
+                all_chunks += cm.pack_chunks_k16
+                units += cm.wpack_bytes // 1024
             self.n_pack_chunks = len(all_chunks)
             # zero-initialised: image rows no pack descriptor covers must read as zero weights
             self.wpack = th.zeros(max(units * 1024, 1024), device=device, dtype=th.uint8)
@@ -179,6 +192,14 @@ class FusedField:
             stash = th.empty(n_tiles * cm.stash_slabs_per_tile * _lib.NB_SLAB_BYTES, device=dev, dtype=th.uint8)
             masks = th.empty(max(n_tiles * cm.mask_words_per_tile * _lib.NB_TILE_ROWS, 1), device=dev, dtype=th.int32)
         cp, cd = self.pe_cfgs()
+        if self.k16_units >= 0 and self.use_two_tile:
+            with th.cuda.device(dev):
+                self._timed("mlp_fwd_train" if training else "mlp_fwd", lambda: check(lib().nerfb200_mlp_fwd2(
+                    C.byref(cm.program), self.wpack.data_ptr() + self.k16_units * 1024, _ptr(self.bias), C.byref(inputs),
+                    C.byref(cp), C.byref(cd), _ptr(self.pe_pos.alpha_tensor()), _ptr(self.pe_dir.alpha_tensor()),
+                    float(self.sigma_bias), _ptr(sigma), _ptr(rgb), _ptr(stash), _ptr(masks), cm.bias_floats,
+                    cm.density_w_off, th.cuda.current_stream().cuda_stream), "mlp_fwd2"))
+            return sigma, rgb, stash, masks
         with th.cuda.device(dev):
             self._timed("mlp_fwd_train" if training else "mlp_fwd", lambda: check(lib().nerfb200_mlp_fwd(
                 C.byref(cm.program), _ptr(self.wpack), _ptr(self.bias), C.byref(inputs), C.byref(cp), C.byref(cd),

@@ -58,6 +58,12 @@ class CompiledMlp:
     mask_words_per_tile: int = 0
     dir_slab: int = SLAB_PE_DIR
     dir_encode_before_op: int = 0
+    # two-tile forward kernel (csrc/mlp_fwd.cu, mlp_fwd2): the main weight chunks once more as
+    # per-K-step images, the density row of the "extra" layer as fp32 weights behind the biases
+    # (it is evaluated by the epilogue of the layer in front), and whether the program qualifies
+    pack_chunks_k16: List[NbPackChunk] = field(default_factory=list)
+    density_w_off: int = -1
+    two_tile_ok: bool = False
 
 
 def nerf_model_layers(lins: dict, n_hidden: int, hidden_dim: int, n_segments: int,
@@ -109,6 +115,9 @@ def compile_forward(layers: List[LayerSpec]) -> CompiledMlp:
     dir_before = (max(pos_uses) + 1) if share and pos_uses else 0   # encoded while that op's MMAs run
     prog.n_slabs, prog.n_stages = (6, 3) if (dir_uses and not share) else (5, 4)
     chunks: List[NbPackChunk] = []
+    chunks_k16: List[NbPackChunk] = []
+    two_tile_ok = (prog.n_slabs == 5)
+    density_w_off = -1
     biases: List[NbPackBias] = []
     w_units = 0          # 1024 B units used in the packed weight buffer
     bias_floats = 0
@@ -169,6 +178,11 @@ def compile_forward(layers: List[LayerSpec]) -> CompiledMlp:
             chunks.append(NbPackChunk(base=lin.w_off + c0, row_stride=lin.in_f, col_stride=1,
                                       n_rows=min(L.out_main, lin.out_f) if L.act != "rgb" else lin.out_f,
                                       n_cols=w, rows_padded=n_main, dst_off=w_units))
+            chunks_k16.append(NbPackChunk(base=lin.w_off + c0, row_stride=lin.in_f, col_stride=1,
+                                          n_rows=min(L.out_main, lin.out_f) if L.act != "rgb" else lin.out_f,
+                                          n_cols=w, rows_padded=n_main, dst_off=w_units, img_rows=int(op.w_rows[ci])))
+            if extra and not split_extra:
+                two_tile_ok = False          # the density row shares the image: old kernel only
             if extra and not split_extra:
                 chunks.append(NbPackChunk(base=lin.w_off + L.out_main * lin.in_f + c0, row_stride=lin.in_f,
                                           col_stride=1, n_rows=1, n_cols=w, rows_padded=16,
@@ -213,6 +227,18 @@ def compile_forward(layers: List[LayerSpec]) -> CompiledMlp:
         if extra:
             biases.append(NbPackBias(base=lin.b_off + L.out_main, n=1, n_padded=16, dst_off=bias_floats, reserved=0))
             bias_floats += 16
+            # two-tile kernel: density = <row out_main of W, input activations> in the epilogue of the
+            # layer in front; needs that input to be exactly the 256 hidden columns of slabs 0..3
+            plain = (li > 0 and len(L.sources) == 1 and L.sources[0].kind == "act" and L.sources[0].width == 256
+                     and lin.in_f == 256 and layers[li - 1].act == "relu" and layers[li - 1].out_main == 256
+                     and density_w_off < 0)
+            if plain:
+                density_w_off = bias_floats
+                biases.append(NbPackBias(base=lin.w_off + L.out_main * lin.in_f, n=256, n_padded=256,
+                                         dst_off=bias_floats, reserved=0))
+                bias_floats += 256
+            else:
+                two_tile_ok = False
         # epilogue
         if L.act == "relu":
             op.epi = _lib.EPI_RELU_SIGMA if extra else _lib.EPI_RELU
@@ -239,7 +265,10 @@ def compile_forward(layers: List[LayerSpec]) -> CompiledMlp:
     return CompiledMlp(program=prog, pack_chunks=chunks, pack_biases=biases,
                        wpack_bytes=w_units * 1024, bias_floats=bias_floats, layers=layers,
                        op_inputs=op_inputs, stash_slabs_per_tile=stash,
-                       mask_words_per_tile=mask_words, dir_slab=dir_slab, dir_encode_before_op=dir_before)
+                       mask_words_per_tile=mask_words, dir_slab=dir_slab, dir_encode_before_op=dir_before,
+                       pack_chunks_k16=chunks_k16, density_w_off=density_w_off,
+                       two_tile_ok=bool(two_tile_ok and bias_floats <= 3072
+                                        and all(L.out_main in (0, 3, 64, 128, 192, 256) or L.act == "rgb" for L in layers)))
 
 
 def to_device_array(items, ctype, device):

@@ -157,3 +157,30 @@ def test_host_stepper_matches_direct_steps(cuda):
     # normalisation can blow up to a full lr-sized step for the odd parameter with a near-zero gradient
     diff = (results["direct"][1] - results["host"][1]).abs()
     assert float((diff > 2e-5).float().mean()) < 1e-3 and float(diff.max()) < 5 * 1e-3
+
+
+@pytest.mark.parametrize("B", [40, 300])
+def test_two_tile_forward_matches_one_tile_kernel(cuda, B):
+    """The experimental two-tiles-in-flight forward kernel (nerfb200_mlp_fwd2: per-K-step weight
+    images in the SWIZZLE_32B layout, density column evaluated by the epilogue) against the
+    default kernel: same outputs, and — through the shared stash / sign-bit layout — the same
+    gradients from the (unchanged) backward kernels.  Odd tile counts and several tile pairs per
+    CTA are covered by the two batch sizes."""
+    o, d, target, idx, pw = _rays(B, 5, 3)
+    outs = {}
+    for two_tile in (False, True):
+        model, cam = _build(cuda, True, 0, 64, seed=2)
+        field = model.model_radiance.fused_field()
+        field.use_two_tile = two_tile
+        th.manual_seed(11)
+        o2, d2, _, _ = cam(idx.to(cuda), o.to(cuda), d.to(cuda))
+        fine, _ = model(o2, d2, pw.to(cuda))
+        loss = th.nn.functional.mse_loss(fine, target.to(cuda))
+        loss.backward()
+        assert (field.k16_units >= 0) and field.compiled.two_tile_ok
+        outs[two_tile] = (fine.detach().clone(), [p.grad.detach().clone() for p in model.model_radiance.parameters()],
+                          cam.translation.grad.detach().clone())
+    assert (outs[True][0] - outs[False][0]).abs().max() < 2e-3          # density: fp32 dot vs MMA accumulation order
+    for ga, gb in zip(outs[True][1], outs[False][1]):
+        assert (ga - gb).norm() <= 2e-2 * gb.norm() + 1e-7
+    assert (outs[True][2] - outs[False][2]).norm() <= 2e-2 * outs[False][2].norm() + 1e-7

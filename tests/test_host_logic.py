@@ -84,7 +84,11 @@ def test_forward_program_of_the_standard_network():
     # every weight element lands in exactly one forward image
     covered = sum(c.n_rows * c.n_cols for c in cm.pack_chunks)
     assert covered == sum(p.numel() for n, p in net.named_parameters() if n.endswith("weight"))
-    assert sum(b.n for b in cm.pack_biases) == sum(p.numel() for n, p in net.named_parameters() if n.endswith("bias"))
+    # every bias once, plus the 256 density weights the two-tile forward kernel reads as fp32
+    assert cm.two_tile_ok and cm.density_w_off >= 0
+    assert sum(b.n for b in cm.pack_biases) == 256 + sum(p.numel() for n, p in net.named_parameters() if n.endswith("bias"))
+    assert len(cm.pack_chunks_k16) == sum(1 for c in cm.pack_chunks if c.rows_padded >= 16 and c.n_rows > 1)
+    assert all(c.img_rows in (16, 128, 256) for c in cm.pack_chunks_k16)
     cb = compile_backward(cm, True, f._encoders())
     assert (cb.pos_grad_cols, cb.dir_grad_cols) == (64, 64)   # canonical encoding-gradient layout
     # the transposed images of an encoding-gradient op cover every (output, encoding column) once,
