@@ -97,6 +97,79 @@ class TrainEngine:
                                            global_mean_scale(self.world), th.cuda.current_stream().cuda_stream), "adam_step")
         self.flat.version += 1     # the packed bf16 weight images are stale now
 
+    # -- checkpoints in the layout Lightning writes for the reference ----------------------------
+    def _param_list(self):
+        return [p for g in self.model.param_groups for p in g["parameters"]]
+
+    def checkpoint(self, epoch: int = 0) -> dict:
+        """The dictionary `Trainer.save_checkpoint` writes for the reference's modules
+        (`ModelCheckpoint`, barf/run_barf.py:142-146): `state_dict` with the reference's keys,
+        `optimizer_states` = the state dict of ONE torch.optim.Adam over `param_groups` (per-parameter
+        `step` / `exp_avg` / `exp_avg_sq`, the order of `configure_optimizers`,
+        barf/model_interpolation.py:543-564) and `lr_schedulers` = SchedulerLeNice's state — so the
+        reference (or `configure_optimizers()` of these modules) resumes from it and this engine
+        resumes from a checkpoint the reference wrote."""
+        params = self._param_list()
+        state, groups, idx = {}, [], 0
+        lrs = self.learning_rates(self.step_count + 1)      # what the scheduler has set for the NEXT step
+        step_t = th.tensor(float(self.step_count))
+        for gi, g in enumerate(self.groups):
+            ids = []
+            for p in self.model.param_groups[gi]["parameters"]:
+                o = self.flat.offset_of(p)
+                if self.step_count > 0:
+                    state[idx] = {"step": step_t.clone(),
+                                  "exp_avg": self.exp_avg[o:o + p.numel()].view(p.shape).detach().cpu().clone(),
+                                  "exp_avg_sq": self.exp_avg_sq[o:o + p.numel()].view(p.shape).detach().cpu().clone()}
+                ids.append(idx)
+                idx += 1
+            groups.append({"lr": lrs[gi], "betas": tuple(self.betas), "eps": self.eps, "weight_decay": g["wd"],
+                           "amsgrad": False, "maximize": False, "foreach": None, "capturable": False,
+                           "differentiable": False, "fused": None, "initial_lr": g["lr0"], "params": ids})
+        assert idx == len(params)
+        sched = {"start_LR": [g["lr0"] for g in self.groups],
+                 "stop_LR": [mg["learning_rate_stop"] for mg in self.model.param_groups],
+                 "number_of_steps": [g["n"] for g in self.groups],
+                 "log_decay_factors": [g["logf"] for g in self.groups],
+                 "decay_factors": [float(th.exp(th.tensor(g["logf"]))) for g in self.groups],
+                 "base_lrs": [g["lr0"] for g in self.groups], "last_epoch": self.step_count,
+                 "_step_count": self.step_count + 1, "_get_lr_called_within_step": False, "_last_lr": lrs}
+        return {"epoch": epoch, "global_step": self.step_count, "pytorch-lightning_version": "2.0.0",
+                "state_dict": {k: v.detach().cpu().clone() for k, v in self.model.state_dict().items()},
+                "optimizer_states": [{"state": state, "param_groups": groups}], "lr_schedulers": [sched],
+                "loops": {}, "callbacks": {}, "hparams_name": "kwargs", "hyper_parameters": {}}
+
+    def save_checkpoint(self, path: str, epoch: int = 0) -> None:
+        th.save(self.checkpoint(epoch), path)
+
+    def load_checkpoint(self, ckpt) -> None:
+        """Resumes from `checkpoint()`'s dictionary, from a file of it, or from a checkpoint
+        Lightning wrote for the reference's module (same keys)."""
+        if isinstance(ckpt, str):
+            ckpt = th.load(ckpt, map_location="cpu", weights_only=False)
+        self.model.load_state_dict(ckpt["state_dict"])
+        self.flat.ensure(self.device)            # load_state_dict copies in place: the views stay valid
+        self.flat.version += 1
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        opt = ckpt["optimizer_states"][0]
+        params = self._param_list()
+        steps = set()
+        for ids, in [(g["params"],) for g in opt["param_groups"]]:
+            for i in ids:
+                st = opt["state"].get(i)
+                if st is None:
+                    continue
+                p = params[i]
+                o = self.flat.offset_of(p)
+                self.exp_avg[o:o + p.numel()].copy_(st["exp_avg"].reshape(-1))
+                self.exp_avg_sq[o:o + p.numel()].copy_(st["exp_avg_sq"].reshape(-1))
+                steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise RuntimeError(f"checkpoint holds parameters at different optimiser steps {sorted(steps)}: "
+                               "the fused Adam keeps one step count")
+        self.step_count = steps.pop() if steps else int(ckpt.get("global_step", 0))
+
     def step(self, o, d, target, img_idx=None, pixel_width=None, coarse_weight: float = 1.0):
         """One optimisation step on this rank's shard of rays; returns the (fine) loss tensor."""
         self.grad.zero_()

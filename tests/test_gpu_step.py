@@ -184,3 +184,79 @@ def test_two_tile_forward_matches_one_tile_kernel(cuda, B):
     for ga, gb in zip(outs[True][1], outs[False][1]):
         assert (ga - gb).norm() <= 2e-2 * gb.norm() + 1e-7
     assert (outs[True][2] - outs[False][2]).norm() <= 2e-2 * outs[False][2].norm() + 1e-7
+
+
+def test_checkpoint_round_trip_and_torch_adam_compatibility(cuda, tmp_path):
+    """engine.save_checkpoint / load_checkpoint in the layout Lightning writes for the reference:
+    (1) 3 steps + save + load into a fresh engine + 2 steps == 5 uninterrupted steps;
+    (2) the optimizer state loads into the torch.optim.Adam + SchedulerLeNice of
+    configure_optimizers() (what the reference resumes with) and one torch step from it equals one
+    engine step."""
+    from nerf_experiments_b200.engine import TrainEngine
+    B = 64
+    batches = [tuple(t.to(cuda) for t in _rays(B, 5, 50 + s)) for s in range(5)]
+
+    def fresh():
+        model, cam = _build(cuda, True, 0, 32, seed=6)
+        return model, cam, TrainEngine(model, cuda)
+
+    model_a, _, eng_a = fresh()
+    th.manual_seed(1)
+    for b in batches:
+        eng_a.step(*b)
+    model_b, _, eng_b = fresh()
+    th.manual_seed(1)
+    for b in batches[:3]:
+        eng_b.step(*b)
+    path = str(tmp_path / "ckpt_epoch=00.ckpt")
+    eng_b.save_checkpoint(path, epoch=0)
+    ck = th.load(path, map_location="cpu", weights_only=False)
+    assert ck["global_step"] == 3 and set(ck["state_dict"]) == set(model_b.state_dict())
+    assert any(k.startswith("model_radiance.model_segments.0.0.") for k in ck["state_dict"])
+    assert {"camera_extrinsics.rotation", "camera_extrinsics.translation"} <= set(ck["state_dict"])
+    rng = th.cuda.get_rng_state(cuda)
+    model_c, cam_c, eng_c = fresh()
+    eng_c.load_checkpoint(path)
+    assert eng_c.step_count == 3
+    th.cuda.set_rng_state(rng, cuda)
+    for b in batches[3:]:
+        eng_c.step(*b)
+    diff = (eng_c.flat.flat - eng_a.flat.flat).abs()
+    assert float((diff > 2e-5).float().mean()) < 1e-3 and float(diff.max()) < 5e-3
+
+    # (2) torch Adam + SchedulerLeNice resume from the same file
+    model_d, cam_d = _build(cuda, True, 0, 32, seed=6)      # no engine: plain autograd gradients
+    model_d.load_state_dict(ck["state_dict"])
+    cfg = model_d.configure_optimizers()
+    opt, sched = cfg["optimizer"], cfg["lr_scheduler"]["scheduler"]
+    opt.load_state_dict(ck["optimizer_states"][0])
+    sched.load_state_dict(ck["lr_schedulers"][0])
+    model_e, cam_e, eng_e = fresh()
+    eng_e.load_checkpoint(ck)
+    # the moments and the step count arrive intact on both sides
+    for pd, pe_ in zip([p for g in opt.param_groups for p in g["params"]],
+                       [p for g in model_e.param_groups for p in g["parameters"]]):
+        off = eng_e.flat.offset_of(pe_)
+        assert float(opt.state[pd]["step"]) == 3.0
+        assert th.equal(opt.state[pd]["exp_avg"].reshape(-1).to(cuda), eng_e.exp_avg[off:off + pe_.numel()])
+        assert th.equal(opt.state[pd]["exp_avg_sq"].reshape(-1).to(cuda), eng_e.exp_avg_sq[off:off + pe_.numel()])
+    o, d, target, idx, pw = batches[3]
+    th.manual_seed(9)
+    opt.zero_grad()
+    o2, d2, _, _ = cam_d(idx, o, d)
+    fine, _ = model_d(o2, d2, pw)
+    th.nn.functional.mse_loss(fine, target).backward()
+    opt.step()
+    sched.step()
+    th.manual_seed(9)
+    eng_e.step(o, d, target, idx, pw)
+    # one step from them is the engine's step: a parameter moves by at most lr = 5e-4, the two
+    # paths agree on all but the odd parameter whose near-zero gradient is dominated by summation order
+    bad = total = 0
+    for (n1, p1), (n2, p2) in zip(model_d.named_parameters(), model_e.named_parameters()):
+        assert n1 == n2
+        bad += int(((p1 - p2).abs() > 5e-5).sum())
+        total += p1.numel()
+        assert (p1 - p2).abs().max() < 6e-4, n1
+    assert bad < 2e-3 * total
+    assert opt.param_groups[0]["lr"] == pytest.approx(eng_e.learning_rates(5)[0], rel=1e-6)
