@@ -434,9 +434,15 @@ resample_icdf_kernel(const float* __restrict__ edges, const float* __restrict__ 
 }
 
 // ---- a12 fast path: Sc <= 64 coarse intervals, Sf <= 256 samples -----------------------------
-// Same arithmetic as resample_icdf_kernel (bit-identical). The targets u_k increase with k and
-// the cdf is sorted, so a lane that owns consecutive samples bisects once and then only walks
-// forward; outputs are staged in shared memory and leave as fully coalesced rows.
+// Same results as resample_icdf_kernel for a sorted cdf (bit-identical), with a third of the
+// instructions: instead of searching a bin for every sample, every BIN finds the first sample
+// that falls into it — the targets u_k are an arithmetic progression, so an approximate
+// division gives a candidate that two exact comparisons with the kernel's own u_k formula fix
+// up — and scatters its index there; a running maximum over the samples (sequential inside a
+// lane, one warp scan across lanes) then hands every sample the last bin that starts at or
+// before it, which is what upper_bound(cdf, u_k) - 1 returns. The interpolation slope is
+// computed once per bin. Outputs are staged in shared memory and leave as coalesced rows.
+template <int PER>   // consecutive samples per lane = ceil(Sf / 32): loops unroll without predicates
 __global__ void __launch_bounds__(kWarps * 32, kFastBlocksPerSm)
 resample_icdf_fast_kernel(const float* __restrict__ edges, const float* __restrict__ cdf,
                           const float* __restrict__ u_ray, int B, int Sc, int Sf,
@@ -444,48 +450,65 @@ resample_icdf_fast_kernel(const float* __restrict__ edges, const float* __restri
   __shared__ float2 s_ec_all[kWarps][kFastSc + 1];      // (edge, cdf)
   __shared__ float s_sc_all[kWarps][kFastSc];           // (e1 - e0) / (c1 - c0) per bin, NaN: empty bin
   __shared__ float s_s_all[kWarps][kFastSf];            // sample centres
-  __shared__ int s_p_all[kWarps][kFastSf];              // bin of every sample (only if requested)
+  __shared__ int s_p_all[kWarps][kFastSf];              // bin starts, then the bin of every sample
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   float2* s_ec = s_ec_all[warp];
   float* s_sc = s_sc_all[warp];
   float* s_s = s_s_all[warp];
   int* s_p = s_p_all[warp];
-  const int per = (Sf + 31) / 32;                       // consecutive samples per lane (<= 8)
+  constexpr int per = PER;
+  const bool full = (Sf == 32 * PER);                   // no ragged last lane: the common shapes
   for (long long ray = (long long)blockIdx.x * kWarps + warp; ray < B;
        ray += (long long)gridDim.x * kWarps) {
     const long long base = ray * (Sc + 1);
     for (int i = lane; i <= Sc; i += 32) s_ec[i] = make_float2(edges[base + i], cdf[base + i]);
+#pragma unroll
+    for (int j = 0; j < PER; ++j) s_p[lane + 32 * j] = 0;   // samples below cdf[1] belong to bin 0
     const float bias = (u_ray != nullptr) ? u_ray[ray] : 0.5f;
     __syncwarp();
-    // the interpolation slope depends on the bin only: one IEEE division per bin (two per lane)
-    // instead of one per sample (six per lane at 64 -> 192), same operands, same result
+    const float u_floor = s_ec[0].y, u_ceil = s_ec[Sc].y;
+    const float u_step = __fdiv_rn(__fsub_rn(u_ceil, u_floor), (float)Sf);
+    const float inv_step = u_step > 0.f ? __frcp_rn(u_step) : 0.f;
+    auto u_of = [&](int k) { return __fadd_rn(u_floor, __fmul_rn(__fadd_rn((float)k, bias), u_step)); };
     for (int i = lane; i < Sc; i += 32) {
       const float2 a = s_ec[i], b = s_ec[i + 1];
       const float dc = __fsub_rn(b.y, a.y);
+      // one IEEE division per bin instead of one per sample: same operands, same result
       s_sc[i] = dc < 1e-10f ? __int_as_float(0x7fc00000) : __fdiv_rn(__fsub_rn(b.x, a.x), dc);
-    }
-    const float u_floor = s_ec[0].y, u_ceil = s_ec[Sc].y;
-    const float u_step = __fdiv_rn(__fsub_rn(u_ceil, u_floor), (float)Sf);
-    const int k0 = lane * per;
-    __syncwarp();
-    int q = 0;   // first index in [0, Sc+1) with cdf > u (upper bound), non-decreasing in k
-    if (k0 < Sf) {
-      const float u = __fadd_rn(u_floor, __fmul_rn(__fadd_rn((float)k0, bias), u_step));
-      int lo = 0, hi = Sc + 1;
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (s_ec[mid].y <= u) lo = mid + 1; else hi = mid;
+      if (i > 0) {
+        // first sample k with cdf[i] <= u_k (u_k is non-decreasing in k)
+        int k = (int)ceilf(fminf(fmaxf((a.y - u_floor) * inv_step - bias, 0.f), (float)Sf));
+        while (k > 0 && u_of(k - 1) >= a.y) --k;
+        while (k < Sf && u_of(k) < a.y) ++k;
+        if (k < Sf) atomicMax(&s_p[k], i);
       }
-      q = lo;
     }
-    for (int j = 0; j < per; ++j) {
+    __syncwarp();
+    // running maximum of the scattered bin starts = bin of every sample
+    const int k0 = lane * per;
+    int loc[PER];
+    int m = 0;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      if (full || k0 + j < Sf) m = max(m, s_p[k0 + j]);
+      loc[j] = m;
+    }
+    int incl = m;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl = max(incl, v);
+    }
+    int before = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) before = 0;
+    __syncwarp();                                        // every lane has read its s_p entries
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
       const int k = k0 + j;
-      if (k < Sf) {
-        const float u = __fadd_rn(u_floor, __fmul_rn(__fadd_rn((float)k, bias), u_step));
-        while (q <= Sc && s_ec[q].y <= u) ++q;
-        int p = q - 1;
-        p = p < 0 ? 0 : (p > Sc - 1 ? Sc - 1 : p);
+      if (full || k < Sf) {
+        const int p = max(loc[j], before);
+        const float u = u_of(k);
         const float2 a = s_ec[p];
         const float scale = s_sc[p];
         float sv;
@@ -500,21 +523,28 @@ resample_icdf_fast_kernel(const float* __restrict__ edges, const float* __restri
     }
     __syncwarp();
     const float e_min = s_ec[0].x, e_max = s_ec[Sc].x;
-    for (int k = lane; k <= Sf; k += 32) {
-      float v;
-      if (Sf == 1) {
-        v = (k == 0) ? e_min : e_max;
-      } else if (k == 0) {
-        v = fmaxf(__fsub_rn(s_s[0], __fmul_rn(__fsub_rn(s_s[1], s_s[0]), 0.5f)), e_min);
-      } else if (k == Sf) {
-        v = fminf(__fadd_rn(s_s[Sf - 1], __fmul_rn(__fsub_rn(s_s[Sf - 1], s_s[Sf - 2]), 0.5f)), e_max);
-      } else {
-        v = __fmul_rn(__fadd_rn(s_s[k - 1], s_s[k]), 0.5f);
+    float* out_row = out_edges + ray * (Sf + 1);
+    if (Sf == 1) {
+      if (lane < 2) st_stream(out_row + lane, lane == 0 ? e_min : e_max);
+    } else {
+      // interior edges: midpoints of neighbouring samples; the two ends by one lane each
+#pragma unroll
+      for (int j = 0; j < PER; ++j) {
+        const int k = lane + 32 * j;
+        if (k >= 1 && (full || k < Sf)) st_stream(out_row + k, __fmul_rn(__fadd_rn(s_s[k - 1], s_s[k]), 0.5f));
       }
-      st_stream(out_edges + ray * (Sf + 1) + k, v);
+      if (lane == 0)
+        st_stream(out_row, fmaxf(__fsub_rn(s_s[0], __fmul_rn(__fsub_rn(s_s[1], s_s[0]), 0.5f)), e_min));
+      if (lane == 1)
+        st_stream(out_row + Sf, fminf(__fadd_rn(s_s[Sf - 1], __fmul_rn(__fsub_rn(s_s[Sf - 1], s_s[Sf - 2]), 0.5f)), e_max));
     }
-    if (out_idx != nullptr)
-      for (int k = lane; k < Sf; k += 32) out_idx[ray * Sf + k] = s_p[k];
+    if (out_idx != nullptr) {
+#pragma unroll
+      for (int j = 0; j < PER; ++j) {
+        const int k = lane + 32 * j;
+        if (full || k < Sf) out_idx[ray * Sf + k] = s_p[k];
+      }
+    }
     __syncwarp();
   }
 }
@@ -570,8 +600,17 @@ extern "C" int nerfb200_resample_icdf(const float* edges, const float* cdf, cons
   NB_CHECK_ARG(edges && cdf && out_edges, "resample_icdf: null pointer");
   if (B == 0) return NERFB200_OK;
   if (Sc <= kFastSc && Sf <= kFastSf) {
-    resample_icdf_fast_kernel<<<warp_grid(B, kFastBlocksPerSm), kWarps * 32, 0, (cudaStream_t)stream>>>(
-        edges, cdf, u_ray, B, Sc, Sf, out_edges, out_idx);
+    const int grid = warp_grid(B, kFastBlocksPerSm);
+#define NB_ICDF_CASE(P)                                                                                  \
+  case P:                                                                                                \
+    resample_icdf_fast_kernel<P><<<grid, kWarps * 32, 0, (cudaStream_t)stream>>>(edges, cdf, u_ray, B, Sc, \
+                                                                                  Sf, out_edges, out_idx);    \
+    break;
+    switch ((Sf + 31) / 32) {
+      NB_ICDF_CASE(1) NB_ICDF_CASE(2) NB_ICDF_CASE(3) NB_ICDF_CASE(4)
+      NB_ICDF_CASE(5) NB_ICDF_CASE(6) NB_ICDF_CASE(7) NB_ICDF_CASE(8)
+    }
+#undef NB_ICDF_CASE
     count_launch();
     NB_CHECK_LAUNCH();
     return NERFB200_OK;
