@@ -214,13 +214,15 @@ int nerfb200_mlp_wgrad(const NbWgradItem* items_dev, int n_items, const void* x_
  *        w.r.t. the PARAMETERS p0 / p1 (the v = p0^2 + 1e-6 chain rule is applied inside);
  *        dsum (F,) or NULL accumulates the column sums of dx, i.e. the bias gradient of the
  *        Linear layer that produced x (saves the separate reduction autograd would launch).
+ *   out_bf16 != 0: y / dx are written as bf16 (N, F) — the operand type of the GEMM that
+ *        consumes them — instead of fp32; inputs, sums and parameter gradients stay fp32.
  */
 enum { NERFB200_ACT_GAUSS = 0, NERFB200_ACT_SARF = 1, NERFB200_ACT_GABOR = 2 };
 int nerfb200_act_fwd(int kind, const float* x, const float* p0, const float* p1, long long N,
-                     int F, float* y, void* stream);
+                     int F, void* y, int out_bf16, void* stream);
 int nerfb200_act_bwd(int kind, const float* x, const float* p0, const float* p1, const float* g,
-                     long long N, int F, float* dx, float* dp0, float* dp1, float* dsum,
-                     void* stream);
+                     long long N, int F, void* dx, float* dp0, float* dp1, float* dsum,
+                     int out_bf16, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * GPU-resident ray batcher. Replaces

@@ -143,8 +143,8 @@ def _declare(L):
                                      C.c_longlong, f32, vp]
     L.nerfb200_pe_fwd.argtypes = [C.POINTER(NbPeCfg), vp, vp, vp, vp, vp, vp, C.c_longlong, vp, vp]
     L.nerfb200_pe_bwd.argtypes = [C.POINTER(NbPeCfg), vp, vp, vp, vp, vp, vp, vp, C.c_longlong, vp, vp, vp]
-    L.nerfb200_act_fwd.argtypes = [i32, vp, vp, vp, C.c_longlong, i32, vp, vp]
-    L.nerfb200_act_bwd.argtypes = [i32, vp, vp, vp, vp, C.c_longlong, i32, vp, vp, vp, vp, vp]
+    L.nerfb200_act_fwd.argtypes = [i32, vp, vp, vp, C.c_longlong, i32, vp, i32, vp]
+    L.nerfb200_act_bwd.argtypes = [i32, vp, vp, vp, vp, C.c_longlong, i32, vp, vp, vp, vp, i32, vp]
     L.nerfb200_ray_batch.argtypes = [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, i32, i32, f32,
                                      vp, vp, vp, vp, vp, vp, vp, vp]
     L.nerfb200_kabsch.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp]

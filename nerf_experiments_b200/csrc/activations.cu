@@ -8,6 +8,7 @@
 //   GABOR  y = exp(-v x^2) cos(s x), v = p0^2 + 1e-6, s = p1 reference gaborf/gabor.py:8-64
 // Thread = one feature column of a chunk of rows: loads are coalesced along the feature axis,
 // the parameter gradient stays in a register until one atomicAdd per thread.
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace nerfb200 {
@@ -28,6 +29,7 @@ struct ActParams {
   float* dp0;
   float* dp1;
   float* dsum;     // optional (F): column sums of dx = bias gradient of the Linear in front
+  int out_bf16;    // y / dx are written as bf16 (the next GEMM's operand type) instead of fp32
   int rows_per_block;
 };
 
@@ -45,6 +47,11 @@ __device__ __forceinline__ float act_forward(int kind, float x, float p0, float 
   }
 }
 
+__device__ __forceinline__ void store_out(float* base, long long i, float v, int out_bf16) {
+  if (out_bf16) reinterpret_cast<__nv_bfloat16*>(base)[i] = __float2bfloat16_rn(v);
+  else st_stream(base + i, v);
+}
+
 constexpr int kActUnroll = 8;   // rows in flight per thread: the kernels are bound by memory-level parallelism
 
 __global__ void __launch_bounds__(kActThreads) act_fwd_kernel(const ActParams p) {
@@ -60,11 +67,11 @@ __global__ void __launch_bounds__(kActThreads) act_fwd_kernel(const ActParams p)
 #pragma unroll
     for (int u = 0; u < kActUnroll; ++u) x[u] = ld_stream(p.x + (r + u) * p.F + f);
 #pragma unroll
-    for (int u = 0; u < kActUnroll; ++u) st_stream(p.y + (r + u) * p.F + f, act_forward(p.kind, x[u], p0, p1));
+    for (int u = 0; u < kActUnroll; ++u) store_out(p.y, (r + u) * p.F + f, act_forward(p.kind, x[u], p0, p1), p.out_bf16);
   }
   for (; r < r1; ++r) {
     const long long i = r * p.F + f;
-    st_stream(p.y + i, act_forward(p.kind, ld_stream(p.x + i), p0, p1));
+    store_out(p.y, i, act_forward(p.kind, ld_stream(p.x + i), p0, p1), p.out_bf16);
   }
 }
 
@@ -124,14 +131,14 @@ __global__ void __launch_bounds__(kActThreads) act_bwd_kernel(const ActParams p)
 #pragma unroll
     for (int u = 0; u < kActUnroll; ++u) {   // same summation order as the row-by-row loop
       const float dx = act_backward(p.kind, x[u], g[u], p0, p1, a0, a1);
-      st_stream(p.dx + (r + u) * p.F + f, dx);
+      store_out(p.dx, (r + u) * p.F + f, dx, p.out_bf16);
       asum += dx;
     }
   }
   for (; r < r1; ++r) {
     const long long i = r * p.F + f;
     const float dx = act_backward(p.kind, ld_stream(p.x + i), ld_stream(p.g + i), p0, p1, a0, a1);
-    st_stream(p.dx + i, dx);
+    store_out(p.dx, i, dx, p.out_bf16);
     asum += dx;
   }
   if (p.kind != NERFB200_ACT_SARF) a0 *= 2.f * p0;   // v = p0^2 + 1e-6
@@ -160,14 +167,15 @@ int launch_shape(long long N, int F, dim3& grid, int& rows_per_block) {
 using namespace nerfb200;
 
 extern "C" int nerfb200_act_fwd(int kind, const float* x, const float* p0, const float* p1,
-                                long long N, int F, float* y, void* stream) {
+                                long long N, int F, void* y, int out_bf16, void* stream) {
   NB_CHECK_ARG(kind >= NERFB200_ACT_GAUSS && kind <= NERFB200_ACT_GABOR, "act_fwd: unknown kind %d", kind);
   NB_CHECK_ARG(N >= 0 && F >= 1, "act_fwd: bad shape N=%lld F=%d", N, F);
   NB_CHECK_ARG(kind != NERFB200_ACT_GABOR || p1, "act_fwd: the Gabor activation needs its spread parameter");
   if (N == 0) return NERFB200_OK;
   NB_CHECK_ARG(x && p0 && y, "act_fwd: null pointer");
   ActParams p{};
-  p.kind = kind; p.x = x; p.p0 = p0; p.p1 = p1; p.N = N; p.F = F; p.y = y;
+  p.kind = kind; p.x = x; p.p0 = p0; p.p1 = p1; p.N = N; p.F = F; p.y = reinterpret_cast<float*>(y);
+  p.out_bf16 = out_bf16;
   dim3 grid;
   launch_shape(N, F, grid, p.rows_per_block);
   act_fwd_kernel<<<grid, kActThreads, 0, (cudaStream_t)stream>>>(p);
@@ -177,15 +185,15 @@ extern "C" int nerfb200_act_fwd(int kind, const float* x, const float* p0, const
 }
 
 extern "C" int nerfb200_act_bwd(int kind, const float* x, const float* p0, const float* p1,
-                                const float* g, long long N, int F, float* dx, float* dp0,
-                                float* dp1, float* dsum, void* stream) {
+                                const float* g, long long N, int F, void* dx, float* dp0,
+                                float* dp1, float* dsum, int out_bf16, void* stream) {
   NB_CHECK_ARG(kind >= NERFB200_ACT_GAUSS && kind <= NERFB200_ACT_GABOR, "act_bwd: unknown kind %d", kind);
   NB_CHECK_ARG(N >= 0 && F >= 1, "act_bwd: bad shape N=%lld F=%d", N, F);
   NB_CHECK_ARG(kind != NERFB200_ACT_GABOR || (p1 && dp1), "act_bwd: the Gabor activation needs p1 and dp1");
   if (N == 0) return NERFB200_OK;
   NB_CHECK_ARG(x && p0 && g && dx && dp0, "act_bwd: null pointer");
   ActParams p{};
-  p.kind = kind; p.x = x; p.p0 = p0; p.p1 = p1; p.g = g; p.N = N; p.F = F; p.dx = dx; p.dp0 = dp0; p.dp1 = dp1; p.dsum = dsum;
+  p.kind = kind; p.x = x; p.p0 = p0; p.p1 = p1; p.g = g; p.N = N; p.F = F; p.dx = reinterpret_cast<float*>(dx); p.dp0 = dp0; p.dp1 = dp1; p.dsum = dsum; p.out_bf16 = out_bf16;
   dim3 grid;
   launch_shape(N, F, grid, p.rows_per_block);
   act_bwd_kernel<<<grid, kActThreads, 0, (cudaStream_t)stream>>>(p);

@@ -6,7 +6,8 @@
 Round-1 status: the Gaussian activations (forward, input / parameter / bias gradients) run in the
 CUDA kernels of csrc/activations.cu; the Linear layers are plain library GEMMs (cuBLAS through
 torch) on the tensor cores with TF32 operands — the precision class the reference trains at
-(`matmul_tf32 = False` on a network restores fp32 GEMMs). The layers are up to 1024 wide, which
+(`matmul_precision = "fp32"` restores fp32 GEMMs, `"bf16"` runs bf16 operands with bf16
+activations between the layers). The layers are up to 1024 wide, which
 does not fit the 256-column tile program of the fused kernel: fusing this network
 is the round-2 item. th.compile of the reference is dropped (no tracing compiler)."""
 from typing import Iterator
@@ -25,26 +26,32 @@ class _GaussNetBase(nn.Module):
         self.gaussian_init_max = gaussian_init_max
         self._parameters_linear: list = []
         self._parameters_gaussian: list = []
-        self.matmul_tf32 = True
+        # GEMM arithmetic: "tf32" (default: fp32 tensors, TF32 tensor-core GEMMs), "bf16" (bf16 operands,
+        # fp32 accumulation and pre-activations, bf16 activations between the layers: measured SLOWER
+        # with cuBLAS, whose bf16-in / fp32-out GEMMs fall back to pre-Blackwell kernels) or "fp32"
+        self.matmul_precision = "tf32"
 
     def _run(self, seq: nn.Sequential, x: th.Tensor) -> th.Tensor:
-        """seq(x) with every Linear (+ GaussAct) pair as one fused-gradient op."""
+        """seq(x) with every Linear (+ GaussAct) pair as one fused-gradient op; fp32 in, fp32 out."""
         mods = list(seq)
-        i = 0
+        n_lin = sum(isinstance(m, nn.Linear) for m in mods)
+        i = seen = 0
         while i < len(mods):
             m = mods[i]
             if isinstance(m, nn.Linear) and x.is_cuda:
+                seen += 1
+                last = seen == n_lin
                 nxt = mods[i + 1] if i + 1 < len(mods) else None
                 if isinstance(nxt, GaussAct):
                     x = ops.linear_activation(x, m.weight, m.bias, _lib.ACT_GAUSS, nxt.inv_standard_deviation,
-                                              None, self.matmul_tf32)
+                                              None, self.matmul_precision, last)
                     i += 2
                     continue
-                x = ops.linear_activation(x, m.weight, m.bias, -1, None, None, self.matmul_tf32)
+                x = ops.linear_activation(x, m.weight, m.bias, -1, None, None, self.matmul_precision, last)
             else:
-                x = m(x)
+                x = m(x.float() if x.dtype == th.bfloat16 else x)
             i += 1
-        return x
+        return x.float() if x.dtype == th.bfloat16 else x
 
     def _create_linear(self, features_in: int, features_out: int) -> nn.Linear:
         linear = nn.Linear(features_in, features_out)

@@ -249,7 +249,7 @@ class _Activation(th.autograd.Function):
         p1c = None if p1 is None else _f32(p1.reshape(-1), "p1", (F,))
         y = th.empty_like(x2)
         with th.cuda.device(x2.device):
-            check(lib().nerfb200_act_fwd(kind, _ptr(x2), _ptr(p0c), _ptr(p1c), x2.shape[0], F, _ptr(y),
+            check(lib().nerfb200_act_fwd(kind, _ptr(x2), _ptr(p0c), _ptr(p1c), x2.shape[0], F, _ptr(y), 0,
                                          _stream()), "act_fwd")
         ctx.kind = kind
         ctx.shape = shape
@@ -266,7 +266,7 @@ class _Activation(th.autograd.Function):
         dp1 = None if p1c is None else th.zeros_like(p1c)
         with th.cuda.device(x2.device):
             check(lib().nerfb200_act_bwd(ctx.kind, _ptr(x2), _ptr(p0c), _ptr(p1c), _ptr(g2), x2.shape[0], F,
-                                         _ptr(dx), _ptr(dp0), _ptr(dp1), None, _stream()), "act_bwd")
+                                         _ptr(dx), _ptr(dp0), _ptr(dp1), None, 0, _stream()), "act_bwd")
         return None, dx.view(ctx.shape), dp0, dp1
 
 
@@ -293,55 +293,78 @@ class _tf32_matmul:
 
 class _LinearActivation(th.autograd.Function):
     """y = act(x W^T + b; p0[, p1]) (kind < 0: no activation).  The GEMMs are library calls
-    (cuBLAS through torch, TF32 tensor cores when `tf32`); the activation, its input gradient,
-    the parameter gradients AND the bias gradient come from one pass of the activation kernels.
+    (cuBLAS through torch); the activation, its input gradient, the parameter gradients AND the
+    bias gradient come from one pass of the activation kernels.  precision:
+      "bf16"  bf16 operands, fp32 accumulation and fp32 pre-activations (the arithmetic of the fused
+              NeRF kernels; the reference's garf/main.py:93 trains in fp16 autocast). The activation
+              kernels then emit y / dz directly as bf16, the operand type of the next GEMM.
+      "tf32"  fp32 tensors, TF32 tensor-core GEMMs (barf/run_barf.py:101).
+      "fp32"  fp32 SIMT GEMMs (tight parity tests).
     Round-1 shape of the GARF networks (their fused tile kernel is round 2)."""
 
     @staticmethod
-    def forward(ctx, kind, tf32, x, weight, bias, p0, p1):
-        x2 = _f32(x.reshape(-1, x.shape[-1]), "x")
-        with _tf32_matmul(tf32):
-            z = th.addmm(bias, x2, weight.t())
+    def forward(ctx, kind, precision, last, x, weight, bias, p0, p1):
+        bf16 = precision == "bf16"
+        x2 = x.reshape(-1, x.shape[-1])
+        if not x2.is_cuda:
+            raise RuntimeError("x: expected a CUDA tensor (nerfb200 has no CPU fallback)")
+        if bf16:
+            xg = x2 if x2.dtype == th.bfloat16 else x2.to(th.bfloat16)
+            wg = weight.to(th.bfloat16)
+            z = th.addmm(bias, xg, wg.t(), out_dtype=th.float32)
+        else:
+            xg, wg = _f32(x2, "x"), weight
+            with _tf32_matmul(precision == "tf32"):
+                z = th.addmm(bias, xg, weight.t())
         F = z.shape[1]
+        out_bf16 = bf16 and not last         # the last layer's output leaves the network in fp32
         if kind >= 0:
             p0c = _f32(p0.reshape(-1), "p0", (F,))
             p1c = None if p1 is None else _f32(p1.reshape(-1), "p1", (F,))
-            y = th.empty_like(z)
+            y = th.empty(z.shape, device=z.device, dtype=th.bfloat16 if out_bf16 else th.float32)
             with th.cuda.device(z.device):
-                check(lib().nerfb200_act_fwd(kind, _ptr(z), _ptr(p0c), _ptr(p1c), z.shape[0], F, _ptr(y), _stream()),
-                      "act_fwd")
-            ctx.save_for_backward(x2, weight, z, p0c, p1c)
+                check(lib().nerfb200_act_fwd(kind, _ptr(z), _ptr(p0c), _ptr(p1c), z.shape[0], F, _ptr(y),
+                                             int(out_bf16), _stream()), "act_fwd")
+            ctx.save_for_backward(xg, wg, z, p0c, p1c)
         else:
-            y = z
-            ctx.save_for_backward(x2, weight, None, None, None)
-        ctx.kind, ctx.tf32, ctx.in_shape = kind, tf32, x.shape
+            y = z.to(th.bfloat16) if out_bf16 else z
+            ctx.save_for_backward(xg, wg, None, None, None)
+        ctx.kind, ctx.precision, ctx.in_shape, ctx.in_dtype = kind, precision, x.shape, x.dtype
         return y.view(*x.shape[:-1], F)
 
     @staticmethod
     def backward(ctx, g):
-        x2, weight, z, p0c, p1c = ctx.saved_tensors
-        F = weight.shape[0]
-        g2 = _f32(g.reshape(-1, F), "g")
+        xg, wg, z, p0c, p1c = ctx.saved_tensors
+        bf16 = ctx.precision == "bf16"
+        F = wg.shape[0]
+        g2 = _f32(g.reshape(-1, F).float(), "g")
         dp0 = dp1 = None
         if ctx.kind >= 0:
-            dz = th.empty_like(z)
+            dz = th.empty(z.shape, device=z.device, dtype=th.bfloat16 if bf16 else th.float32)
             dp0 = th.zeros_like(p0c)
             dp1 = None if p1c is None else th.zeros_like(p1c)
             db = th.zeros(F, device=z.device, dtype=th.float32)
             with th.cuda.device(z.device):
                 check(lib().nerfb200_act_bwd(ctx.kind, _ptr(z), _ptr(p0c), _ptr(p1c), _ptr(g2), z.shape[0], F,
-                                             _ptr(dz), _ptr(dp0), _ptr(dp1), _ptr(db), _stream()), "act_bwd")
+                                             _ptr(dz), _ptr(dp0), _ptr(dp1), _ptr(db), int(bf16), _stream()), "act_bwd")
         else:
-            dz = g2
-            db = g2.sum(0) if ctx.needs_input_grad[4] else None
-        with _tf32_matmul(ctx.tf32):
-            dx = (dz @ weight).view(ctx.in_shape) if ctx.needs_input_grad[2] else None
-            dw = dz.t() @ x2 if ctx.needs_input_grad[3] else None
-        return None, None, dx, dw, db, dp0, dp1
+            db = g2.sum(0) if ctx.needs_input_grad[5] else None
+            dz = g2.to(th.bfloat16) if bf16 else g2
+        dx = dw = None
+        if bf16:
+            if ctx.needs_input_grad[3]:
+                dx = th.mm(dz, wg, out_dtype=th.float32).view(ctx.in_shape)
+            if ctx.needs_input_grad[4]:
+                dw = th.mm(dz.t(), xg, out_dtype=th.float32)
+        else:
+            with _tf32_matmul(ctx.precision == "tf32"):
+                dx = (dz @ wg).view(ctx.in_shape) if ctx.needs_input_grad[3] else None
+                dw = dz.t() @ xg if ctx.needs_input_grad[4] else None
+        return None, None, None, dx, dw, db, dp0, dp1
 
 
-def linear_activation(x, weight, bias, kind: int = -1, p0=None, p1=None, tf32: bool = True):
-    return _LinearActivation.apply(kind, tf32, x, weight, bias, p0, p1)
+def linear_activation(x, weight, bias, kind: int = -1, p0=None, p1=None, precision: str = "tf32", last: bool = False):
+    return _LinearActivation.apply(kind, precision, last, x, weight, bias, p0, p1)
 
 
 # ---------------------------------------------------------------------------------------------

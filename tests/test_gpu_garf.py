@@ -69,14 +69,18 @@ def _seeded_nets(cuda):
     return prop.to(cuda), rad.to(cuda)
 
 
-@pytest.mark.parametrize("tf32", [False, True])
-def test_garf_networks_match_reference(cuda, tf32):
-    """fp32 GEMMs: tight against the reference's fp32 outputs / gradients.  TF32 GEMMs (the default, the
-    reference's own matmul precision class): rgb within the north-star 1e-2, gradients to a few per cent."""
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+def test_garf_networks_match_reference(cuda, precision):
+    """fp32 GEMMs: tight against the reference's fp32 outputs / gradients.  TF32 and bf16-operand GEMMs
+    (bf16 is the default: the arithmetic of the fused NeRF kernels; the reference trains GARF in fp16
+    autocast): rgb within the north-star 1e-2, gradients to a few per cent (rel-L2 per tensor for bf16)."""
     g = _g()
     prop, rad = _seeded_nets(cuda)
-    prop.matmul_tf32 = rad.matmul_tf32 = tf32
+    prop.matmul_precision = rad.matmul_precision = precision
+    tf32 = precision != "fp32"
     rtol, atol, grtol, gatol = (1e-4, 1e-5, 5e-3, 2e-5) if not tf32 else (2e-2, 1e-2, 6e-2, 5e-3)
+    if precision == "bf16":
+        rtol, grtol, gatol = 5e-2, 0.5, 5e-2
     rgb, dens = rad(g["net_pos"].to(cuda), g["net_dir"].to(cuda))
     assert th.allclose(rgb.cpu(), g["rad_rgb"], rtol=rtol, atol=atol)
     assert th.allclose(dens.cpu(), g["rad_density"], rtol=rtol, atol=atol)
@@ -98,7 +102,7 @@ def test_garf_model_chain_matches_oracle(cuda, training):
     th.backends.cuda.matmul.allow_tf32 = False
     th.manual_seed(3)
     m = GarfModel(2.0, 7.0, 32, 48, 0.5, 1.5, 1.0, 1e-3, 1e-4, 100, 0.0, 1e-3, 1e-4, 100, 0.0).to(cuda)
-    m.proposal_network.matmul_tf32 = m.radiance_network.matmul_tf32 = False   # tight comparison: fp32 GEMMs
+    m.proposal_network.matmul_precision = m.radiance_network.matmul_precision = "fp32"   # tight comparison
     m.train(training)
     B = 24
     gen = th.Generator().manual_seed(11)
