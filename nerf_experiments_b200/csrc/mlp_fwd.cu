@@ -151,18 +151,21 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdParams p) {
       //      direction slab when it has one of its own (otherwise it shares slab 4 and is written
       //      later). All MMAs of the previous tile have completed (its last accumulator was read).
       {
+        NB_TRACE(392, threadIdx.x == 0);
         if (training) drain.acquire_mask(sm.slab_drained, sched.start_mask, lane);
-        if (cq == 0) {
+        NB_TRACE(393, threadIdx.x == 0);
+        {   // all four threads of a row share the work (a coordinate each + the identity columns)
           PeSample ps;
           load_sample(p.in, n, ps);
-          encode_to_slab(p.pe_pos, sm.mask_pos, ps, sm, row);
-        } else if (cq == 1 && dir_at_start) {
-          PeSample pd;       // the direction encoder sees the direction as its "position"
-          load_sample(p.in, n, pd);
-          pd.x[0] = pd.dir[0]; pd.x[1] = pd.dir[1]; pd.x[2] = pd.dir[2];
-          encode_to_slab(p.pe_dir, sm.mask_dir, pd, sm, row);
+          if (p.pe_pos.slab >= 0) encode_to_slab_split(p.pe_pos, sm.mask_pos, ps, sm.slab(p.pe_pos.slab), row, cq);
+          if (dir_at_start) {   // the direction encoder sees the direction as its "position"
+            ps.x[0] = ps.dir[0]; ps.x[1] = ps.dir[1]; ps.x[2] = ps.dir[2];
+            encode_to_slab_split(p.pe_dir, sm.mask_dir, ps, sm.slab(p.pe_dir.slab), row, cq);
+          }
         }
+        NB_TRACE(394, threadIdx.x == 0);
         signal_slabs(sm.slab_ready, sched.start_mask, lane);
+        NB_TRACE(395, threadIdx.x == 0);
         if (training) drain.produced(stashed(-1, sched.start_mask));
       }
 
@@ -175,12 +178,23 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdParams p) {
           // The direction encoding takes over the slab the position encoding no longer needs
           // (its last reader was op oi-1, whose accumulator these threads have already seen).
           if (training) drain.acquire_mask(sm.slab_drained, sched.reencode_mask, lane);
+#ifdef NB_EXP_REENCODE_SPLIT
+          {
+            PeSample pd;
+            load_sample(p.in, n, pd);
+            pd.x[0] = pd.dir[0]; pd.x[1] = pd.dir[1]; pd.x[2] = pd.dir[2];
+            encode_to_slab_split(p.pe_dir, sm.mask_dir, pd, sm.slab(p.pe_dir.slab), row, cq);
+          }
+#else
+          // one quarter does it alone (a third of the position encoding's work, mid-tile): the split
+          // version makes all sixteen warps wait at its barrier and measured slower in training
           if (cq == 1) {
             PeSample pd;
             load_sample(p.in, n, pd);
             pd.x[0] = pd.dir[0]; pd.x[1] = pd.dir[1]; pd.x[2] = pd.dir[2];
             encode_to_slab(p.pe_dir, sm.mask_dir, pd, sm, row);
           }
+#endif
           signal_slabs(sm.slab_ready, sched.reencode_mask, lane);
           if (training && p.pe_dir.stash_slab >= 0) drain.produced(sched.reencode_mask);
         }

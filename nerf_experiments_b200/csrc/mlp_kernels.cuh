@@ -317,6 +317,25 @@ __device__ __forceinline__ void encode_to_slab_at(const NbPeCfg& cfg, const floa
   });
 }
 
+// The same, split over the four threads of a row (cq = column quarter = threadIdx.x >> 7): every
+// thread clears its 16-column quarter, a named barrier over the row threads orders the clears
+// before the element stores, then quarter c < 3 encodes coordinate c and quarter 3 the identity
+// columns. One thread per row used to do all of it: ~15 k cycles per tile on a single warp per
+// scheduler (nine sincosf, sixty 2-byte stores and nothing to hide their latency behind).
+// Must be called by ALL row threads (the barrier counts kRowThreads).
+__device__ __forceinline__ void encode_to_slab_split(const NbPeCfg& cfg, const float* mask, const PeSample& s,
+                                                     uint8_t* slab, int row, int cq) {
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+    *reinterpret_cast<uint4*>(slab + (uint32_t)row * 128u + ((uint32_t)((2 * cq + q) ^ (row & 7)) << 4)) =
+        make_uint4(0u, 0u, 0u, 0u);
+  named_bar_sync(1, kRowThreads);
+  pe_encode(cfg, mask, s, [&](int col, float v) {
+    *reinterpret_cast<__nv_bfloat16*>(slab + tc::slab_offset((uint32_t)row, (uint32_t)col)) =
+        __float2bfloat16_rn(v);
+  }, cq < 3 ? (1 << cq) : 8);
+}
+
 // Writes the encoding of one sample as bf16 into row `row` of the encoder's slab (zero padded).
 __device__ __forceinline__ void encode_to_slab(const NbPeCfg& cfg, const float* mask,
                                                const PeSample& s, const MlpSmem& sm, int row) {

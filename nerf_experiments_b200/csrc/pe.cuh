@@ -69,10 +69,14 @@ __device__ __forceinline__ PeIpe pe_ipe_prepare(const NbPeCfg& cfg, const PeSamp
   return r;
 }
 
-// Calls emit(column, value) for every column of the encoding of one sample.
+// Calls emit(column, value) for the columns of the encoding of one sample selected by `parts`:
+// bit c (c = 0..2) = the cos / sin columns of coordinate c, bit 3 = the identity columns. The
+// fused kernels split a row over four threads that way (kPeAll = everything); the value of a
+// column does not depend on who computes it.
+constexpr int kPeAll = 15;
 template <typename Emit>
 __device__ __forceinline__ void pe_encode(const NbPeCfg& cfg, const float* mask,
-                                          const PeSample& s, Emit emit) {
+                                          const PeSample& s, Emit emit, int parts = kPeAll) {
   float x[3] = {s.x[0], s.x[1], s.x[2]};
   PeIpe ipe;
   if (cfg.kind == NB_PE_INTEGRATED) {
@@ -82,13 +86,14 @@ __device__ __forceinline__ void pe_encode(const NbPeCfg& cfg, const float* mask,
   }
   int col = 0;
   if (cfg.include_identity || cfg.kind == NB_PE_IDENTITY) {
-    emit(0, x[0]); emit(1, x[1]); emit(2, x[2]);
+    if (parts & 8) { emit(0, x[0]); emit(1, x[1]); emit(2, x[2]); }
     col = 3;
   }
   if (cfg.kind == NB_PE_IDENTITY) return;
   const int L = cfg.levels;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
+    if (!((parts >> c) & 1)) continue;
     float sn = 0.f, cs = 1.f;
     float lvl = 1.f;  // 4^j
     float freq = cfg.scale;
