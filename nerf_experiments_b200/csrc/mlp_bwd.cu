@@ -135,7 +135,9 @@ mlp_bwd_kernel(const __grid_constant__ MlpBwdParams p) {
       }
       // All MMAs of the previous tile are complete (its last accumulator was read); slab 0 may be
       // rewritten once its stash copy has drained.
+      NB_TRACE(392, threadIdx.x == 0);
       drain.acquire_mask(sm.slab_drained, sched.start_mask, lane);
+      NB_TRACE(393, threadIdx.x == 0);
 
       // ---- head: gradients w.r.t. the pre-activations of the output layer (quarter 0) ----
       float d_sigma_pre = 0.f;
@@ -164,7 +166,9 @@ mlp_bwd_kernel(const __grid_constant__ MlpBwdParams p) {
           *reinterpret_cast<uint4*>(slab + (uint32_t)row * 128u + ((uint32_t)(q ^ (row & 7)) << 4)) =
               make_uint4(0u, 0u, 0u, 0u);
       }
+      NB_TRACE(394, threadIdx.x == 0);
       signal_slabs(sm.slab_ready, sched.start_mask, lane);
+      NB_TRACE(395, threadIdx.x == 0);
       drain.produced(sched.start_mask);
 
       // this thread's share of the gradients w.r.t. the query position / direction of the row
@@ -269,6 +273,7 @@ mlp_bwd_kernel(const __grid_constant__ MlpBwdParams p) {
       }
 
       // ---- d(position), d(direction) of the samples -> rays (the four quarters add up) ----
+      NB_TRACE(396, threadIdx.x == 0);
       if (p.want_input_grads) {
         if (p.in.pos != nullptr) {
           if (valid) {

@@ -39,6 +39,10 @@ for i in range(min(n_ops, 16)):
     a, b, c, dd = [t[i * 4 + k].item() - base for k in range(4)]
     ch = [(t[128 + i * 8 + k].item() - base, t[256 + i * 8 + k].item() - base) for k in range(min(prog.ops[i].n_chunks, 8))]
     print(f"{i:2d} | {a:7d} {b:7d} {c:7d} {dd:7d} | {b-a:6d} {c-b:6d} {dd-c:6d} | " + " ".join(f"({x},{y})" for x, y in ch))
+if which == "bwd":
+    e = [t[392 + k].item() - base for k in range(5)]
+    print("tile start (thread 0): tile_done seen", e[0], "| drain waited +", e[1] - e[0], "| head gradient +", e[2] - e[1],
+          "| published +", e[3] - e[2], "| ops done (ray-gradient reduction starts) at", e[4])
 if which == "fwd":
     e = [t[392 + k].item() - base for k in range(4)]
     print("tile start (thread 0): tile_done seen", e[0], "| drain waited +", e[1] - e[0], "| encoded +", e[2] - e[1], "| published +", e[3] - e[2])
