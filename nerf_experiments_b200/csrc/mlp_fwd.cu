@@ -567,10 +567,10 @@ mlp_fwd2_kernel(const __grid_constant__ MlpFwd2Params pp) {
         const long long n_raw = (long long)(2 * pair + t) * NB_TILE_ROWS + row;
         const long long n = n_raw < p.N ? n_raw : (long long)p.N - 1;
         wait_drained(t);
-        if (cq == 0 && p.pe_pos.slab >= 0) {
+        if (p.pe_pos.slab >= 0) {   // all four threads of a row share the work
           PeSample ps;
           load_sample(p.in, n, ps);
-          encode_to_slab_at(p.pe_pos, sm.mask_pos, ps, sm.slab(t, p.pe_pos.slab), row);
+          encode_to_slab_split(p.pe_pos, sm.mask_pos, ps, sm.slab(t, p.pe_pos.slab), row, cq);
         }
         publish(t, true);
         dr_pending[t] = training && t2_stash_mask(p, reencode_op, -1) != 0u;
