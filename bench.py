@@ -69,7 +69,7 @@ class ClockSampler:
                     self.samples.append(parts)
             except Exception:  # noqa: BLE001
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.02)     # nvidia-smi itself takes ~30 ms: ~20 samples per second of load
 
     def __enter__(self):
         self._thread.start()
@@ -155,14 +155,17 @@ def run_ours(args):
     # ---- device-resident timed region -----------------------------------------------------
     field.timers = {}
     launches0 = _lib.launch_count()
-    with ClockSampler(local) as clocks:
-        barrier()
-        e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(K):
-            loss = eng.step(*batches[W + i])
-        e1.record()
-        barrier()
+    # clocks / throttle reasons are sampled from here to the end of the end-to-end region below: both
+    # timed regions (and nothing but the few milliseconds between them) run under the sampler
+    clocks = ClockSampler(local)
+    clocks.__enter__()
+    barrier()
+    e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        loss = eng.step(*batches[W + i])
+    e1.record()
+    barrier()
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count() - launches0
     timers = field.timers
@@ -189,6 +192,7 @@ def run_ours(args):
     losses.append(stepper.flush())                                  # D2H read of the last step's loss
     e1.record()
     barrier()
+    clocks.__exit__(None, None, None)
     last = losses[-1]
     assert len(losses) == K
     t_e2e = th.tensor([e0.elapsed_time(e1)], device=dev)
@@ -376,10 +380,16 @@ def emit_json(obj):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
+    # defaults: 100 timed steps of ~3.3 ms for our arm (enough for ~10 clock samples), 3 steps of the
+    # bounded CPU sample for the reference arm
+    if args.steps is None:
+        args.steps = 100 if args.impl == "ours" else 3
+    if args.warmup is None:
+        args.warmup = 10 if args.impl == "ours" else 1
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
         # launched directly: re-launch one rank per GPU (the driver uses the same torchrun line)
