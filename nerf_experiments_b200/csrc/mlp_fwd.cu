@@ -5,11 +5,12 @@
 // (reference barf/model_interpolation.py:288-312, barf/model_interpolation_architecture.py:96-141)
 // — 12 cuBLAS GEMMs + ~40 elementwise launches in the reference — by one persistent launch.
 //
-// CTA = 11 warps: warps 0-7 row threads (TMEM lane = tile row, two column halves), warp 8
-// issues MMAs, warp 9 streams weight images through the ring, warp 10 copies activation slabs
-// to the HBM stash (training). Consecutive layers alternate between two TMEM accumulator
-// buffers and hand activations over slab by slab, so the tensor pipe works on layer l+1 while
-// the row threads are still in the epilogue of layer l (see mlp_kernels.cuh).
+// CTA = 19 warps: warps 0-15 row threads (TMEM lane = tile row, four 16-column quarters of every
+// slab), warp 16 issues MMAs, warp 17 streams weight images through the ring, warp 18 copies
+// activation slabs to the HBM stash (training). Consecutive layers alternate between two TMEM
+// accumulator buffers and hand activations over slab by slab, so the tensor pipe works on
+// layer l+1 while the row threads are still in the epilogue of layer l (see mlp_kernels.cuh).
+// nerfb200_mlp_fwd2 at the end of the file is the experimental two-tiles-in-flight variant.
 #include <type_traits>
 #include "common.cuh"
 #include "mlp.h"

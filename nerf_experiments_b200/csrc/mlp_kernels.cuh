@@ -95,7 +95,7 @@ static_assert((2 * NB_MAX_RING_STAGES + 2 * kMaxSlabs + 5) * 8 + 4 <= 256, "cont
 // ---- who writes which slab when ----------------------------------------------------------------
 // Every role of the CTA replays the same production schedule of a tile: "phase -1" is the tile
 // start (encodings / head gradient), phase oi is what the row threads write around op oi's
-// epilogue. A production of slab s = one completion of slab_ready[s] (all eight row warps arrive,
+// epilogue. A production of slab s = one completion of slab_ready[s] (all sixteen row warps arrive,
 // whether or not they wrote part of it).
 struct TileSchedule {
   uint32_t start_mask;      // slabs written at tile start
