@@ -267,6 +267,14 @@ int nerfb200_adam_step(float* params, const float* grads, float* exp_avg, float*
                        const long long* group_end_host, const float* group_lr_host,
                        const float* group_wd_host, float beta1, float beta2, float eps,
                        long long step, float grad_scale, void* stream);
+/* The same step with its schedule in DEVICE memory: sched_dev = [1 - beta1^step, sqrt(1 - beta2^step),
+ * lr of every group] (2 + n_groups floats, written by the caller before the launch). A launch captured
+ * in a CUDA graph then follows the learning-rate schedule and the bias correction across replays. */
+int nerfb200_adam_step_sched(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                             long long n, int n_groups, const long long* group_begin_host,
+                             const long long* group_end_host, const float* group_wd_host,
+                             const float* sched_dev, float beta1, float beta2, float eps,
+                             float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -15,10 +15,20 @@ struct AdamGroups {
   float weight_decay[NERFB200_MAX_ADAM_GROUPS];
 };
 
+// sched (optional, DEVICE): [bias_c1, sqrt(bias_c2), lr[0..n_groups)] of this step — read from memory
+// instead of the launch parameters, so that a launch captured in a CUDA graph follows the schedule
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
             float* __restrict__ v, long long n, AdamGroups groups, float beta1, float beta2,
-            float eps, float bias_c1, float bias_c2_sqrt, float grad_scale) {
+            float eps, float bias_c1, float bias_c2_sqrt, float grad_scale,
+            const float* __restrict__ sched) {
+  if (sched != nullptr) {
+    bias_c1 = sched[0];
+    bias_c2_sqrt = sched[1];
+#pragma unroll
+    for (int q = 0; q < NERFB200_MAX_ADAM_GROUPS; ++q)
+      if (q < groups.n_groups) groups.lr[q] = sched[2 + q];
+  }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     float lr = 0.f, wd = 0.f;
@@ -73,7 +83,33 @@ extern "C" int nerfb200_adam_step(float* params, const float* grads, float* exp_
   const int cap = sm_count() * 8;
   if (blocks > cap) blocks = cap;
   adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, gr, beta1,
-                                                        beta2, eps, (float)bc1, (float)sqrt(bc2), grad_scale);
+                                                        beta2, eps, (float)bc1, (float)sqrt(bc2), grad_scale, nullptr);
+  count_launch();
+  NB_CHECK_LAUNCH();
+  return NERFB200_OK;
+}
+
+extern "C" int nerfb200_adam_step_sched(float* params, const float* grads, float* exp_avg,
+                                        float* exp_avg_sq, long long n, int n_groups,
+                                        const long long* group_begin_host, const long long* group_end_host,
+                                        const float* group_wd_host, const float* sched_dev, float beta1,
+                                        float beta2, float eps, float grad_scale, void* stream) {
+  NB_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && sched_dev && n >= 0, "adam_step_sched: null pointer");
+  NB_CHECK_ARG(n_groups >= 1 && n_groups <= NERFB200_MAX_ADAM_GROUPS, "adam_step_sched: n_groups=%d", n_groups);
+  if (n == 0) return NERFB200_OK;
+  AdamGroups gr;
+  gr.n_groups = n_groups;
+  for (int q = 0; q < NERFB200_MAX_ADAM_GROUPS; ++q) {
+    gr.begin[q] = q < n_groups ? group_begin_host[q] : 0;
+    gr.end[q] = q < n_groups ? group_end_host[q] : 0;
+    gr.lr[q] = 0.f;
+    gr.weight_decay[q] = q < n_groups ? group_wd_host[q] : 0.f;
+  }
+  int blocks = ceil_div(n, 256);
+  const int cap = sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, gr, beta1,
+                                                        beta2, eps, 1.f, 1.f, grad_scale, sched_dev);
   count_launch();
   NB_CHECK_LAUNCH();
   return NERFB200_OK;

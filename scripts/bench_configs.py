@@ -47,7 +47,22 @@ if "c1" in which:   # vanilla NeRF as run_vanilla_as_barf.py: PE 10/4 without id
     o, d, tgt, idx, pw = rays(1024)
     ms = timeit(lambda: eng.step(o, d, tgt, None, pw))
     out["c1_vanilla_1024x64"] = {"ms_per_step": round(ms, 4), "rays_per_s": round(1024 / ms * 1e3)}
+    eng.capture(o, d, tgt, None, pw)          # the same step as one CUDA graph
+    ms = timeit(lambda: eng.replay(o, d, tgt, None, pw))
+    out["c1_vanilla_1024x64_cuda_graph"] = {"ms_per_step": round(ms, 4), "rays_per_s": round(1024 / ms * 1e3),
+                                            "library_launches_per_step": int(eng.launches_per_replay)}
     print(out, flush=True)
+    # C2 (the bench.py workload) eager vs graph, for reference
+    import bench
+    m2 = bench.build_model(20)
+    e2 = TrainEngine(m2, dev)
+    o2, d2, t2, i2, p2 = rays(4096)
+    ms_e = timeit(lambda: e2.step(o2, d2, t2, i2, p2))
+    e2.capture(o2, d2, t2, i2, p2)
+    ms_g = timeit(lambda: e2.replay(o2, d2, t2, i2, p2))
+    out["c2_barf_4096x128_eager_vs_graph"] = {"ms_eager": round(ms_e, 4), "ms_graph": round(ms_g, 4)}
+    print(out, flush=True)
+    del e2, m2
 
 if "c3" in which:   # Mip-BARF: integrated encoding, ONE network as proposal and radiance model, poses
     from nerf_experiments_b200.model_mip import MipBarf

@@ -260,3 +260,30 @@ def test_checkpoint_round_trip_and_torch_adam_compatibility(cuda, tmp_path):
         assert (p1 - p2).abs().max() < 6e-4, n1
     assert bad < 2e-3 * total
     assert opt.param_groups[0]["lr"] == pytest.approx(eng_e.learning_rates(5)[0], rel=1e-6)
+
+
+def test_captured_step_matches_eager_steps(cuda):
+    """TrainEngine.capture / replay (the whole optimisation step as one CUDA graph, Adam's schedule read
+    from device memory) == eager step(): same losses and parameters over several steps whose learning
+    rates differ (no random sampling offsets in this configuration, so the two runs see the same rays)."""
+    from nerf_experiments_b200.engine import TrainEngine
+    B = 96
+    batches = [tuple(t.to(cuda) for t in _rays(B, 5, 70 + s)) for s in range(6)]
+    out = {}
+    for mode in ("eager", "graph"):
+        model, cam = _build(cuda, True, 0, 32, seed=8, sampling="equidistant", offset=0.0)
+        eng = TrainEngine(model, cuda)
+        losses = [float(eng.step(*batches[0]))]
+        if mode == "graph":
+            eng.capture(*batches[0])
+            assert eng.launches_per_replay >= 7          # pack, pose, sampling, field fwd/bwd/wgrad, compositing, Adam ...
+            for b in batches[1:]:
+                losses.append(float(eng.replay(*b)))
+        else:
+            for b in batches[1:]:
+                losses.append(float(eng.step(*b)))
+        out[mode] = (losses, eng.flat.flat.detach().clone(), eng.step_count)
+    assert out["eager"][2] == out["graph"][2] == 6
+    assert out["eager"][0] == pytest.approx(out["graph"][0], rel=1e-4)
+    diff = (out["eager"][1] - out["graph"][1]).abs()
+    assert float((diff > 2e-5).float().mean()) < 1e-3 and float(diff.max()) < 5e-3
