@@ -71,29 +71,33 @@ def _seeded_nets(cuda):
 
 @pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
 def test_garf_networks_match_reference(cuda, precision):
-    """fp32 GEMMs: tight against the reference's fp32 outputs / gradients.  TF32 and bf16-operand GEMMs
-    (bf16 is the default: the arithmetic of the fused NeRF kernels; the reference trains GARF in fp16
-    autocast): rgb within the north-star 1e-2, gradients to a few per cent (rel-L2 per tensor for bf16)."""
+    """Against the reference modules' fp32 outputs / gradients.  fp32 GEMMs: element-wise tight.  TF32 (the
+    default; the reference's own matmul precision class) and bf16 operands: rgb well inside the north-star
+    1e-2 and every parameter gradient within a small relative L2 error (measured on B200: TF32 rgb 1e-4,
+    gradients <= 1.2e-3; bf16 rgb 7e-4, gradients <= 1e-2 — scripts/garf_precision.py)."""
     g = _g()
     prop, rad = _seeded_nets(cuda)
     prop.matmul_precision = rad.matmul_precision = precision
-    tf32 = precision != "fp32"
-    rtol, atol, grtol, gatol = (1e-4, 1e-5, 5e-3, 2e-5) if not tf32 else (2e-2, 1e-2, 6e-2, 5e-3)
-    if precision == "bf16":
-        rtol, grtol, gatol = 5e-2, 0.5, 5e-2
+    out_atol, out_rtol, grad_rel = {"fp32": (1e-5, 1e-4, None), "tf32": (1e-3, 2e-3, 5e-3), "bf16": (5e-3, 1e-2, 3e-2)}[precision]
+
+    def check_grads(net, prefix):
+        for n, p in net.named_parameters():
+            ref = g[prefix + n]
+            got = _thin(p.grad).cpu()
+            if grad_rel is None:
+                assert th.allclose(got, ref, rtol=5e-3, atol=2e-5 * float(ref.abs().max() + 1)), n
+            else:
+                assert float((got - ref).norm()) <= grad_rel * float(ref.norm()) + 1e-7, n
+
     rgb, dens = rad(g["net_pos"].to(cuda), g["net_dir"].to(cuda))
-    assert th.allclose(rgb.cpu(), g["rad_rgb"], rtol=rtol, atol=atol)
-    assert th.allclose(dens.cpu(), g["rad_density"], rtol=rtol, atol=atol)
+    assert th.allclose(rgb.cpu(), g["rad_rgb"], rtol=out_rtol, atol=out_atol)
+    assert th.allclose(dens.cpu(), g["rad_density"], rtol=out_rtol, atol=out_atol)
     ((rgb * g["up_rgb"].to(cuda)).sum() + (dens * g["up_density"].to(cuda)).sum()).backward()
-    for n, p in rad.named_parameters():
-        ref = g["rad.grad." + n]
-        assert th.allclose(_thin(p.grad).cpu(), ref, rtol=grtol, atol=gatol * float(ref.abs().max() + 1)), n
+    check_grads(rad, "rad.grad.")
     sp = prop(g["net_pos"].to(cuda))
-    assert th.allclose(sp.cpu(), g["prop_sigma"], rtol=rtol, atol=atol)
+    assert th.allclose(sp.cpu(), g["prop_sigma"], rtol=out_rtol, atol=out_atol)
     (sp * g["up_prop"].to(cuda)).sum().backward()
-    for n, p in prop.named_parameters():
-        ref = g["prop.grad." + n]
-        assert th.allclose(_thin(p.grad).cpu(), ref, rtol=grtol, atol=gatol * float(ref.abs().max() + 1)), n
+    check_grads(prop, "prop.grad.")
 
 
 @pytest.mark.parametrize("training", [True, False])
