@@ -287,3 +287,32 @@ def test_captured_step_matches_eager_steps(cuda):
     assert out["eager"][0] == pytest.approx(out["graph"][0], rel=1e-4)
     diff = (out["eager"][1] - out["graph"][1]).abs()
     assert float((diff > 2e-5).float().mean()) < 1e-3 and float(diff.max()) < 5e-3
+
+
+def test_two_tile_entry_point_rejects_programs_it_cannot_run(cuda):
+    """nerfb200_mlp_fwd2 validates the tile program: a 6-slab program (direction encoded next to the
+    position, not delayed) comes back as an argument error with a message, not as a launch."""
+    import ctypes as C
+    from nerf_experiments_b200 import _lib
+    from nerf_experiments_b200 import model_interpolation_architecture as arch
+    from nerf_experiments_b200 import positional_encodings as pe
+    from nerf_experiments_b200.fused_mlp import make_inputs
+    th.manual_seed(0)
+    net = arch.NerfModel(2, 256, False, False, 1, pe.BarfPositionalEncoding(10, 10.0, 0.0, 0.0, True, 1.0),
+                         pe.BarfPositionalEncoding(4, 4.0, 0.0, 0.0, True, 1.0)).to(cuda)
+    f = net.fused_field()
+    cm = f.prepare(cuda)
+    assert cm.program.n_slabs == 6 and not cm.two_tile_ok and f.k16_units < 0
+    n = 256
+    pos = th.randn((n, 3), device=cuda)
+    inputs = make_inputs(n, 1, 0, pos=pos, dir=pos, pixel_width_per_sample=True)
+    sigma, rgb = th.empty(n, device=cuda), th.empty((n, 3), device=cuda)
+    cp, cd = f.pe_cfgs()
+    rc = _lib.lib().nerfb200_mlp_fwd2(C.byref(cm.program), f.wpack.data_ptr(), f.bias.data_ptr(), C.byref(inputs),
+                                      C.byref(cp), C.byref(cd), f.pe_pos.alpha_tensor().data_ptr(),
+                                      f.pe_dir.alpha_tensor().data_ptr(), 0.0, sigma.data_ptr(), rgb.data_ptr(),
+                                      None, None, cm.bias_floats, cm.density_w_off, th.cuda.current_stream().cuda_stream)
+    assert rc != 0 and b"mlp_fwd2" in _lib.lib().nerfb200_last_error()
+    # the default entry point runs the same program
+    s2, r2 = net(pos, pos, None, None, None)
+    assert th.isfinite(s2).all() and th.isfinite(r2).all()
