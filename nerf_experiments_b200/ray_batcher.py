@@ -138,3 +138,18 @@ def render_image(model, origins: th.Tensor, directions: th.Tensor, height: int, 
         pw = th.full((o.shape[0], 1), pixel_width, device=o.device)
         out.append(model.forward(o, d, pw)[0])
     return th.cat(out).view(height, width, 3).clamp(0, 1)
+
+
+@th.no_grad()
+def render_image_sharded(model, origins: th.Tensor, directions: th.Tensor, height: int, width: int,
+                         pixel_width: float, chunk: int = 16384, group=None, dst: int = 0):
+    """`render_image` with the image rows split over the ranks of a process group (every rank holds
+    the model; rank `dst` receives the (H, W, 3) image, the others None) — config 5 of BASELINE.json:
+    the 800 x 800 render sharded over 1 / 2 / 4 / 8 GPUs."""
+    from .parallel import render_rows_sharded
+
+    def rows(r0: int, r1: int) -> th.Tensor:
+        o, d = origins[r0 * width: r1 * width], directions[r0 * width: r1 * width]
+        return render_image(model, o, d, r1 - r0, width, pixel_width, chunk)
+
+    return render_rows_sharded(rows, height, width, origins.device, group, dst)

@@ -196,3 +196,35 @@ def test_gloo_two_ranks_gradient_allreduce_equals_full_batch():
     th.nn.functional.mse_loss(rgb, target).backward()
     assert th.allclose(got[0], got[1])
     assert th.allclose(got[0], w.grad, rtol=1e-5, atol=1e-8)
+
+
+def _sharded_render_worker(rank, world, port, out):
+    import torch.distributed as dist
+    from nerf_experiments_b200.parallel import render_rows_sharded
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    H, W = 7, 5                                     # 7 rows over 2 ranks: ragged blocks
+    full = th.arange(H * W * 3, dtype=th.float32).view(H, W, 3)
+    img = render_rows_sharded(lambda a, b: full[a:b].clone(), H, W, th.device("cpu"), None, 0)
+    if rank == 0:
+        out.put(bool(th.equal(img, full)))
+    else:
+        out.put(img is None)
+    dist.destroy_process_group()
+
+
+def test_sharded_render_assembles_the_rows_of_all_ranks():
+    """2-rank gloo: every rank renders its block of rows, rank 0 gets the image, the others None."""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_sharded_render_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p_ in procs:
+        p_.start()
+    results = [out.get(timeout=120) for _ in procs]
+    for p_ in procs:
+        p_.join(timeout=60)
+    assert results == [True, True]
