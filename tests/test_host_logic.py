@@ -148,11 +148,11 @@ def test_shard_ranges_partition_the_batch():
         assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
 
 
-def _gloo_worker(rank, world, port, q):
+def _gloo_worker(rank, world, init, q):
     import torch.distributed as dist
     from nerf_experiments_b200.parallel import allreduce_sum_, global_mean_scale, shard_range
     from oracle import ref_render
-    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    dist.init_process_group("gloo", init_method=init, rank=rank, world_size=world)
     # data-parallel gradient of a mean loss over rays == all-reduced shard gradients / world
     g = th.Generator().manual_seed(0)
     B, S = 16, 8
@@ -172,13 +172,19 @@ def _gloo_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_gloo_two_ranks_gradient_allreduce_equals_full_batch():
+def _file_rendezvous(tmp_path, name):
+    """file:// rendezvous: no TCP port to collide with a neighbour or a socket in TIME_WAIT"""
+    os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")
+    return f"file://{tmp_path / name}"
+
+
+def test_gloo_two_ranks_gradient_allreduce_equals_full_batch(tmp_path):
     import torch.multiprocessing as mp
     from oracle import ref_render
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + os.getpid() % 2000
-    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    init = _file_rendezvous(tmp_path, "rdzv_allreduce")
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, init, q)) for r in range(2)]
     for p in procs:
         p.start()
     got = dict(q.get(timeout=120) for _ in range(2))
@@ -198,10 +204,10 @@ def test_gloo_two_ranks_gradient_allreduce_equals_full_batch():
     assert th.allclose(got[0], w.grad, rtol=1e-5, atol=1e-8)
 
 
-def _sharded_render_worker(rank, world, port, out):
+def _sharded_render_worker(rank, world, init, out):
     import torch.distributed as dist
     from nerf_experiments_b200.parallel import render_rows_sharded
-    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    dist.init_process_group("gloo", init_method=init, rank=rank, world_size=world)
     H, W = 7, 5                                     # 7 rows over 2 ranks: ragged blocks
     full = th.arange(H * W * 3, dtype=th.float32).view(H, W, 3)
     img = render_rows_sharded(lambda a, b: full[a:b].clone(), H, W, th.device("cpu"), None, 0)
@@ -212,16 +218,13 @@ def _sharded_render_worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_sharded_render_assembles_the_rows_of_all_ranks():
+def test_sharded_render_assembles_the_rows_of_all_ranks(tmp_path):
     """2-rank gloo: every rank renders its block of rows, rank 0 gets the image, the others None."""
-    import socket
     import torch.multiprocessing as mp
-    with socket.socket() as sk:
-        sk.bind(("127.0.0.1", 0))
-        port = sk.getsockname()[1]
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
-    procs = [ctx.Process(target=_sharded_render_worker, args=(r, 2, port, out)) for r in range(2)]
+    init = _file_rendezvous(tmp_path, "rdzv_render")
+    procs = [ctx.Process(target=_sharded_render_worker, args=(r, 2, init, out)) for r in range(2)]
     for p_ in procs:
         p_.start()
     results = [out.get(timeout=120) for _ in procs]
