@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define NERFB200_ABI_VERSION 1
+#define NERFB200_ABI_VERSION 2   /* 2: act_fwd/act_bwd take out_bf16 (+ dsum), NbPackChunk.img_rows, mlp_fwd2, adam_step_sched, kabsch, ray_batch */
 
 enum {
   NERFB200_OK = 0,

@@ -93,6 +93,7 @@ class NbWgradItem(C.Structure):
 
 
 _lib = None
+ABI_VERSION = 2      # include/nerfb200.h: NERFB200_ABI_VERSION
 
 
 def build(verbose: bool = False) -> str:
@@ -114,6 +115,9 @@ def lib() -> C.CDLL:
                 f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(there is no CPU fallback)")
         _lib = C.CDLL(LIB_PATH)
+        if _lib.nerfb200_abi_version() != ABI_VERSION:
+            raise RuntimeError(f"{LIB_PATH} implements ABI version {_lib.nerfb200_abi_version()}, this package binds "
+                               f"version {ABI_VERSION}: rebuild it (python -c 'import __graft_entry__ as g; g.build()')")
         _lib.nerfb200_last_error.restype = C.c_char_p
         _lib.nerfb200_launch_count.restype = C.c_longlong
         _declare(_lib)
