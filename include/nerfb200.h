@@ -8,7 +8,8 @@
  *   - every call is stream-ordered on `stream` (a cudaStream_t passed as void*), allocates
  *     nothing, never synchronises and never throws; it returns 0 on success or a
  *     NERFB200_ERR_* code, with the text retrievable through nerfb200_last_error();
- *   - workspaces are caller-owned and sized by the matching *_workspace_bytes() call.
+ *   - workspaces (activation / gradient stashes, sign-bit masks) are caller-owned; the fused-field
+ *     entry points state their sizes (nerfb200_mlp_workspace_bytes, nerfb200_garf_workspace_bytes).
  *
  * Each entry point cites the reference interface it replaces (paths relative to the
  * reference repository root).
@@ -25,7 +26,7 @@
 extern "C" {
 #endif
 
-#define NERFB200_ABI_VERSION 2   /* 2: act_fwd/act_bwd take out_bf16 (+ dsum), NbPackChunk.img_rows, mlp_fwd2, adam_step_sched, kabsch, ray_batch */
+#define NERFB200_ABI_VERSION 3   /* 3: adam_step_dev replaces adam_step_sched; GARF fused field; render_rays; trans_cdf / prop_loss */
 
 enum {
   NERFB200_OK = 0,
@@ -267,14 +268,28 @@ int nerfb200_adam_step(float* params, const float* grads, float* exp_avg, float*
                        const long long* group_end_host, const float* group_lr_host,
                        const float* group_wd_host, float beta1, float beta2, float eps,
                        long long step, float grad_scale, void* stream);
-/* The same step with its schedule in DEVICE memory: sched_dev = [1 - beta1^step, sqrt(1 - beta2^step),
- * lr of every group] (2 + n_groups floats, written by the caller before the launch). A launch captured
- * in a CUDA graph then follows the learning-rate schedule and the bias correction across replays. */
-int nerfb200_adam_step_sched(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
-                             long long n, int n_groups, const long long* group_begin_host,
-                             const long long* group_end_host, const float* group_wd_host,
-                             const float* sched_dev, float beta1, float beta2, float eps,
-                             float grad_scale, void* stream);
+/* The whole optimiser step driven from DEVICE memory, so that a launch captured in a CUDA graph
+ * needs no host work per step: `state` = 3 int64 (zero-initialised by the caller): [0] steps taken,
+ * [1] steps skipped, [2] scratch. The kernel evaluates every group's learning-rate schedule in
+ * closed form for step state[0] + 1 — SchedulerLeNice (barf/model_interpolation.py:30-67) or
+ * ExponentialLR, lr0 * gamma^(step - 1) (garf/model_garf.py:365-428) — and Adam's
+ * bias corrections for state[0] + 1 - state[1], then advances the counters. When `loss_flag` (one
+ * float, may be NULL) is NaN or infinite the step is a no-op for parameters and moments, as in the
+ * reference, whose NaN loss is replaced by a fresh leaf so that no parameter receives a gradient
+ * (barf/model_interpolation.py:522-524); the skipped step still advances the schedules. */
+enum { NERFB200_LR_LE_NICE = 0, NERFB200_LR_EXPONENTIAL = 1 };
+typedef struct {
+  long long begin, end;      /* [begin, end) floats of the flat buffer                         */
+  long long n_steps;         /* LE_NICE: lr0 * exp(log_factor * min(step, n_steps)); EXPONENTIAL: unused */
+  float lr0;                 /* learning_rate_start                                             */
+  float log_factor;          /* LE_NICE: (ln stop - ln start) / n; EXPONENTIAL: ln gamma        */
+  float weight_decay;
+  int32_t mode;              /* NERFB200_LR_*                                                   */
+} NbAdamGroup;
+int nerfb200_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                           long long n, const NbAdamGroup* groups_host, int n_groups, float beta1,
+                           float beta2, float eps, float grad_scale, const float* loss_flag,
+                           long long* state, void* stream);
 
 #ifdef __cplusplus
 }

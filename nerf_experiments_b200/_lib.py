@@ -92,8 +92,15 @@ class NbWgradItem(C.Structure):
                 ("bias_dst", C.c_int32)]
 
 
+class NbAdamGroup(C.Structure):
+    _fields_ = [("begin", C.c_longlong), ("end", C.c_longlong), ("n_steps", C.c_longlong), ("lr0", C.c_float),
+                ("log_factor", C.c_float), ("weight_decay", C.c_float), ("mode", C.c_int32)]
+
+
+LR_LE_NICE, LR_EXPONENTIAL = 0, 1
+
 _lib = None
-ABI_VERSION = 2      # include/nerfb200.h: NERFB200_ABI_VERSION
+ABI_VERSION = 3      # include/nerfb200.h: NERFB200_ABI_VERSION
 
 
 def build(verbose: bool = False) -> str:
@@ -145,7 +152,8 @@ def _declare(L):
     L.nerfb200_mlp_wgrad.argtypes = [vp, i32, vp, i32, vp, i32, vp, vp]
     L.nerfb200_adam_step.argtypes = [vp, vp, vp, vp, C.c_longlong, i32, vp, vp, vp, vp, f32, f32, f32,
                                      C.c_longlong, f32, vp]
-    L.nerfb200_adam_step_sched.argtypes = [vp, vp, vp, vp, C.c_longlong, i32, vp, vp, vp, vp, f32, f32, f32, f32, vp]
+    L.nerfb200_adam_step_dev.argtypes = [vp, vp, vp, vp, C.c_longlong, C.POINTER(NbAdamGroup), i32, f32, f32, f32,
+                                         f32, vp, vp, vp]
     L.nerfb200_pe_fwd.argtypes = [C.POINTER(NbPeCfg), vp, vp, vp, vp, vp, vp, C.c_longlong, vp, vp]
     L.nerfb200_pe_bwd.argtypes = [C.POINTER(NbPeCfg), vp, vp, vp, vp, vp, vp, vp, C.c_longlong, vp, vp, vp]
     L.nerfb200_act_fwd.argtypes = [i32, vp, vp, vp, C.c_longlong, i32, vp, i32, vp]
@@ -166,7 +174,7 @@ EXPORTS = [
     "nerfb200_resample_alloc", "nerfb200_resample_fallback", "nerfb200_resample_icdf",
     "nerfb200_pose_fwd", "nerfb200_pose_bwd", "nerfb200_so3_to_SO3",
     "nerfb200_mlp_pack", "nerfb200_mlp_fwd", "nerfb200_mlp_fwd2", "nerfb200_mlp_bwd", "nerfb200_mlp_wgrad", "nerfb200_pe_fwd", "nerfb200_pe_bwd",
-    "nerfb200_adam_step", "nerfb200_adam_step_sched", "nerfb200_act_fwd", "nerfb200_act_bwd", "nerfb200_ray_batch", "nerfb200_kabsch",
+    "nerfb200_adam_step", "nerfb200_adam_step_dev", "nerfb200_act_fwd", "nerfb200_act_bwd", "nerfb200_ray_batch", "nerfb200_kabsch",
 ]
 
 

@@ -144,7 +144,7 @@ mlp_bwd_kernel(const __grid_constant__ MlpBwdParams p) {
       if (cq <= 1) {
         const float sg = p.sigma[n];
         if (valid && p.g_sigma != nullptr)
-          d_sigma_pre = p.g_sigma[n] * (sg > 8.f ? 1.f : (1.f - __expf(-sg)));
+          d_sigma_pre = p.g_sigma[n] * (sg > 8.f ? 1.f : -expm1f(-sg));   // sigmoid(x) = 1 - exp(-softplus(x)), without cancellation for tiny densities
       }
       if (cq == 0) {
         float d4[4] = {0.f, 0.f, 0.f, 0.f};

@@ -50,10 +50,25 @@ namespace {
 __global__ void __launch_bounds__(256)
 pose_fwd_kernel(const float* __restrict__ rotation, const float* __restrict__ translation,
                 const int32_t* __restrict__ img_idx, const float* __restrict__ o,
-                const float* __restrict__ d, int B, float* __restrict__ out_o,
+                const float* __restrict__ d, int B, int n_images, float* __restrict__ out_o,
                 float* __restrict__ out_d, float* __restrict__ out_R, float* __restrict__ out_t) {
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < B; r += gridDim.x * blockDim.x) {
     const int i = img_idx[r];
+    if ((unsigned)i >= (unsigned)n_images) {
+      // the reference raises IndexError on the host; a stream-ordered call cannot, so the ray is
+      // poisoned instead: NaN outputs make the loss NaN (visible, and the guarded optimiser skips
+      // the step) and nothing is read or written out of bounds
+      const float q = __int_as_float(0x7fc00000);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        out_o[3 * r + c] = q;
+        out_d[3 * r + c] = q;
+        if (out_t != nullptr) out_t[3 * r + c] = q;
+      }
+      if (out_R != nullptr)
+        for (int c = 0; c < 9; ++c) out_R[9 * (size_t)r + c] = q;
+      continue;
+    }
     const float wx = __ldg(rotation + 3 * i), wy = __ldg(rotation + 3 * i + 1),
                 wz = __ldg(rotation + 3 * i + 2);
     const float tx = __ldg(translation + 3 * i), ty = __ldg(translation + 3 * i + 1),
@@ -83,10 +98,11 @@ pose_fwd_kernel(const float* __restrict__ rotation, const float* __restrict__ tr
 __global__ void __launch_bounds__(256)
 pose_bwd_kernel(const float* __restrict__ rotation, const int32_t* __restrict__ img_idx,
                 const float* __restrict__ d, const float* __restrict__ g_o,
-                const float* __restrict__ g_d, int B, float* __restrict__ d_rotation,
+                const float* __restrict__ g_d, int B, int n_images, float* __restrict__ d_rotation,
                 float* __restrict__ d_translation) {
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < B; r += gridDim.x * blockDim.x) {
     const int i = img_idx[r];
+    if ((unsigned)i >= (unsigned)n_images) continue;   // poisoned in the forward pass; never scatter out of bounds
     const float wx = __ldg(rotation + 3 * i), wy = __ldg(rotation + 3 * i + 1),
                 wz = __ldg(rotation + 3 * i + 2);
     float R[9];
@@ -143,7 +159,7 @@ extern "C" int nerfb200_pose_fwd(const float* rotation, const float* translation
   NB_CHECK_ARG(rotation && translation && img_idx && o && d && out_o && out_d, "pose_fwd: null pointer");
   if (B == 0) return NERFB200_OK;
   pose_fwd_kernel<<<grid1d(B), 256, 0, (cudaStream_t)stream>>>(rotation, translation, img_idx, o, d,
-                                                               B, out_o, out_d, out_R, out_t);
+                                                               B, n_images, out_o, out_d, out_R, out_t);
   count_launch();
   NB_CHECK_LAUNCH();
   return NERFB200_OK;
@@ -157,7 +173,7 @@ extern "C" int nerfb200_pose_bwd(const float* rotation, const int32_t* img_idx, 
                "pose_bwd: null pointer");
   if (B == 0) return NERFB200_OK;
   pose_bwd_kernel<<<grid1d(B), 256, 0, (cudaStream_t)stream>>>(rotation, img_idx, d, g_o, g_d, B,
-                                                               d_rotation, d_translation);
+                                                               n_images, d_rotation, d_translation);
   count_launch();
   NB_CHECK_LAUNCH();
   return NERFB200_OK;

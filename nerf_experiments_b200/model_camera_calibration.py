@@ -72,10 +72,15 @@ class CameraCalibrationModel(NerfInterpolation):
 
     def _train_origins(self):
         dataset = self._loop().datamodule.dataset_train
-        img_idxs = th.tensor([dataset.index_to_index[i] for i in range(dataset.n_images)],
-                             device=self.device, dtype=th.int32)
-        origs_raw = dataset.camera_origins.to(self.device)
-        origs_noisy = dataset.camera_origins_noisy.to(self.device)
+        cache = getattr(self, "_origin_cache", None)
+        if cache is None or cache[0] is not dataset:
+            # built once per dataset: the step then issues no host-to-device copy (and can be captured)
+            img_idxs = th.tensor([dataset.index_to_index[i] for i in range(dataset.n_images)],
+                                 device=self.device, dtype=th.int64)
+            cache = (dataset, img_idxs, dataset.camera_origins.to(self.device).contiguous(),
+                     dataset.camera_origins_noisy.to(self.device).contiguous())
+            self._origin_cache = cache
+        _, img_idxs, origs_raw, origs_noisy = cache
         origs_pred, _ = self.camera_extrinsics.forward_origins(img_idxs, origs_noisy)
         return origs_raw, origs_pred
 
@@ -114,6 +119,54 @@ class BarfModel(CameraCalibrationModel):
         if sigma < 1 / 4:
             return th.tensor([0.], device=alpha.device)
         return sigma
+
+    # -- the training step split for the engine: host-side schedules / device-only loss ------------
+    def update_schedules(self, step: int) -> None:
+        """Host part of a training step (barf/model_barf.py:36-47): coarse-to-fine alpha of both
+        encoders from the fractional epoch and the blur level of the targets, written in place to
+        device memory the kernels read — so the device part below can live in a CUDA graph."""
+        loop = self._loop()
+        epoch = step / len(loop.train_dataloader)
+        self.model_radiance.position_encoder.update_alpha(epoch)
+        self.model_radiance.direction_encoder.update_alpha(epoch)
+        enc = self.model_radiance.position_encoder
+        sigma = float(BarfModel.get_sigma_alpha(th.tensor(enc.alpha_value), self.max_gaussian_sigma))
+        dm = loop.datamodule
+        lo, hi, coef = dm.blur_levels(sigma)
+        w = [0.0] * dm.n_sigmas
+        if lo == hi:
+            w[lo] = 1.0
+        else:
+            w[lo], w[hi] = coef, 1.0 - coef
+        if getattr(self, "_blur_w", None) is None or self._blur_w.numel() != dm.n_sigmas:
+            self._blur_w = th.zeros(dm.n_sigmas, device=self.device)
+            self._blur_w_host = th.zeros(dm.n_sigmas).pin_memory()
+        if getattr(self, "_blur_w_last", None) != w:         # the level changes rarely: no copy otherwise
+            self._blur_w_host.copy_(th.tensor(w))
+            self._blur_w.copy_(self._blur_w_host, non_blocking=True)
+            self._blur_w_last = w
+        self._sigma_value = sigma
+
+    def training_loss(self, o_raw, o_noisy, d_raw, d_noisy, colors, img_idx, pixel_width):
+        """Device part of BarfModel.training_step (barf/model_barf.py:29-92) on the reference's 7-tuple
+        whose colours are the raw blur pyramid (B, n_sigmas, 3): pose transform, blurred targets, render,
+        loss, PSNR and the per-step pose error (Kabsch alignment) — no host synchronisation."""
+        cam = self.camera_extrinsics
+        o_pred, d_pred, _, _ = cam(img_idx, o_noisy, d_noisy)
+        blurred = (colors * self._blur_w.view(1, -1, 1)).sum(dim=1) if colors.shape[1] == self._blur_w.numel() \
+            else colors[:, 0]
+        fine, coarse = self.forward(o_pred, d_pred, pixel_width)
+        loss_fine = nn.functional.mse_loss(fine, blurred)
+        loss = loss_fine
+        logs = {"loss_fine": loss_fine.detach(), "train_psnr": self.psnr_tensor(loss_fine),
+                "alpha": self.model_radiance.position_encoder.alpha}
+        if self.proposal:
+            loss_coarse = nn.functional.mse_loss(coarse, blurred)
+            loss = loss_fine + loss_coarse
+            logs["train_loss_coarse"] = loss_coarse.detach()
+        with th.no_grad():
+            logs["pose_error"] = self.compute_pose_error()
+        return loss, logs
 
     def _step_helper(self, batch, batch_idx, purpose: Literal["train", "val"]):
         loop = self._loop()
@@ -174,7 +227,7 @@ class MipNeRF(NerfInterpolation):
             loss = loss + loss_coarse * 0.1
             logs[f"{purpose}_loss_coarse"] = loss_coarse
         self.log_dict(logs)
-        return loss
+        return self._nan_guard(loss)      # barf/model_mip.py:78-80
 
 
 class MipBarf(CameraCalibrationModel):
@@ -251,4 +304,4 @@ class MipBarf(CameraCalibrationModel):
         if (purpose == "train" and batch_idx % 100 == 0) or (purpose == "val" and batch_idx == 0):
             logs["pose_error"] = self.compute_pose_error()
         self.log_dict(logs)
-        return loss
+        return self._nan_guard(loss)      # barf/model_mip.py:300-302

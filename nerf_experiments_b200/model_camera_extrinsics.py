@@ -31,4 +31,6 @@ class CameraExtrinsics(NerfBaseModel):
 
     def forward(self, i: th.Tensor, o: th.Tensor, d: th.Tensor):
         """(o + t_i, R_i d, R_i, t_i)."""
-        return ops.pose_forward(self.rotation, self.translation, i, o, d)
+        # `grad_sink` (set by engine.TrainEngine): the backward kernel accumulates the pose gradients
+        # straight into the engine's flat gradient buffer
+        return ops.pose_forward(self.rotation, self.translation, i, o, d, getattr(self, "grad_sink", None))

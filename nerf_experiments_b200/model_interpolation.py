@@ -169,9 +169,18 @@ class NerfInterpolation(LightningModule):
             loss = loss + loss_coarse
             logs[f"{purpose}_loss_coarse"] = loss_coarse
         self.log_dict(logs)
-        # the reference replaces a NaN loss by a constant so that the step is a no-op (:522-524);
-        # same effect without the host sync
-        loss = th.where(th.isnan(loss), th.ones_like(loss), loss)
+        return self._nan_guard(loss)
+
+    @staticmethod
+    def _nan_guard(loss: th.Tensor) -> th.Tensor:
+        """The reference's guard, verbatim in effect (barf/model_interpolation.py:522-524): a NaN loss
+        is replaced by a fresh leaf, so backward reaches no parameter and the optimiser skips the step.
+        This is the path Lightning's automatic optimisation drives, and like the reference it reads
+        the loss back (one host sync); engine.TrainEngine applies the same rule on the device instead
+        (nerfb200_adam_step_dev skips the step when the all-reduced loss is not finite)."""
+        if loss.isnan():
+            loss = th.tensor(1., requires_grad=True)
+            warnings.warn("loss was nan - no optimization step performed")
         return loss
 
     def validation_transform_rays(self, ray_origs, ray_dirs, transform_params=None):

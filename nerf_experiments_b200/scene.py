@@ -89,6 +89,7 @@ class SyntheticScene:
     n_images: int
     height: int
     width: int
+    batcher: object = None    # GpuRayBatcher over the images + blur pyramid (make_scene(blur_sigmas=...))
 
     @property
     def n_rays(self):
@@ -106,10 +107,35 @@ def so3_exp(w: th.Tensor) -> th.Tensor:
 
 
 @th.no_grad()
+def gaussian_blur_pyramid(images: th.Tensor, sigmas) -> th.Tensor:
+    """(N, H, W, 3) -> (N, H, W, n_sigmas, 3): one separable Gaussian blur per sigma, sigmas <= 0.25
+    kept as the original image (what ImagePoseDataset.gaussian_blur builds with PIL,
+    reference barf/dataset.py:251-270; a data-generation helper, not a parity-critical path)."""
+    x = images.permute(0, 3, 1, 2).contiguous()
+    levels = []
+    for sigma in sigmas:
+        if sigma <= 0.25:
+            levels.append(x)
+            continue
+        r = max(int(math.ceil(3 * sigma)), 1)
+        k = th.exp(-0.5 * (th.arange(-r, r + 1, device=x.device, dtype=th.float32) / sigma) ** 2)
+        k = (k / k.sum()).view(1, 1, -1)
+        c = x.shape[1]
+        y = th.nn.functional.pad(x, (r, r, 0, 0), mode="replicate")
+        y = th.nn.functional.conv2d(y, k.view(1, 1, 1, -1).expand(c, 1, 1, -1), groups=c)
+        y = th.nn.functional.pad(y, (0, 0, r, r), mode="replicate")
+        y = th.nn.functional.conv2d(y, k.view(1, 1, -1, 1).expand(c, 1, -1, 1), groups=c)
+        levels.append(y)
+    return th.stack(levels, dim=1).permute(0, 3, 4, 1, 2).contiguous()
+
+
 def make_scene(n_images: int, height: int, width: int, device, seed: int = 134534,
-               rotation_noise: float = 0.0, translation_noise: float = 0.0, radius: float = 4.0):
+               rotation_noise: float = 0.0, translation_noise: float = 0.0, radius: float = 4.0,
+               blur_sigmas=None):
     """Renders the scene from n_images seeded poses; the stored rays use poses perturbed by
-    N(0, noise^2) in so(3) and translation (the BARF setting, reference barf/run_barf.py:27-30)."""
+    N(0, noise^2) in so(3) and translation (the BARF setting, reference barf/run_barf.py:27-30).
+    With `blur_sigmas` (decreasing, last = 0: the reference's `gaussian_blur_sigmas`) the scene also
+    carries a `ray_batcher.GpuRayBatcher` over the images and their blur pyramid (`scene.batcher`)."""
     g = th.Generator().manual_seed(seed)
     c2w = look_at_poses(n_images, radius, g)
     focal = width / 2 / math.tan(CAMERA_ANGLE_X / 2)
@@ -125,6 +151,13 @@ def make_scene(n_images: int, height: int, width: int, device, seed: int = 13453
         O.append(o); D.append(d); On.append(on); Dn.append(dn)
         Cs.append(shade_rays(o, d))
         Is.append(th.full((o.shape[0],), k, device=device, dtype=th.int32))
-    return SyntheticScene(origins=th.cat(On), directions=th.cat(Dn), origins_true=th.cat(O),
-                          directions_true=th.cat(D), colors=th.cat(Cs), image_index=th.cat(Is),
-                          pixel_width=1.0 / focal, n_images=n_images, height=height, width=width)
+    sc = SyntheticScene(origins=th.cat(On), directions=th.cat(Dn), origins_true=th.cat(O),
+                        directions_true=th.cat(D), colors=th.cat(Cs), image_index=th.cat(Is),
+                        pixel_width=1.0 / focal, n_images=n_images, height=height, width=width)
+    sc.c2w, sc.c2w_noisy, sc.focal = c2w, c2w_noisy, focal
+    if blur_sigmas is not None:
+        from .ray_batcher import GpuRayBatcher
+        images = sc.colors.view(n_images, height, width, 3)
+        sc.batcher = GpuRayBatcher(gaussian_blur_pyramid(images, list(blur_sigmas)), c2w, focal, c2w_noisy,
+                                   list(blur_sigmas), device=device)
+    return sc

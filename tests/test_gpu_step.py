@@ -316,3 +316,95 @@ def test_two_tile_entry_point_rejects_programs_it_cannot_run(cuda):
     # the default entry point runs the same program
     s2, r2 = net(pos, pos, None, None, None)
     assert th.isfinite(s2).all() and th.isfinite(r2).all()
+
+
+def test_non_finite_loss_makes_the_step_a_no_op(cuda):
+    """The reference replaces a NaN loss by a fresh leaf, so the optimiser moves nothing
+    (barf/model_interpolation.py:522-524). The engine applies the same rule on the device: parameters and
+    both Adam moments stay bit-identical, the schedules advance, Adam's per-parameter step does not."""
+    from nerf_experiments_b200.engine import TrainEngine
+    B = 64
+    model, cam = _build(cuda, True, 0, 32, seed=3)
+    eng = TrainEngine(model, cuda)
+    good = [tuple(t.to(cuda) for t in _rays(B, 5, 40 + s)) for s in range(3)]
+    eng.step(*good[0])
+    snap = [t.clone() for t in (eng.flat.flat, eng.exp_avg, eng.exp_avg_sq)]
+    o, d, target, idx, pw = [t.clone() for t in good[1]]
+    o[7, 1] = float("nan")                                  # one poisoned ray
+    loss = eng.step(o, d, target, idx, pw)
+    assert th.isnan(loss)
+    for a, b in zip(snap, (eng.flat.flat, eng.exp_avg, eng.exp_avg_sq)):
+        assert th.equal(a, b)
+    assert eng.step_count == 2 and eng.skipped_steps() == 1 and eng.state[:2].tolist() == [2, 1]
+    # an out-of-range image index poisons its ray instead of reading / scattering out of bounds
+    bad_idx = idx.clone(); bad_idx[3] = 99
+    assert th.isnan(eng.step(good[1][0], good[1][1], target, bad_idx, pw))
+    for a, b in zip(snap, (eng.flat.flat, eng.exp_avg, eng.exp_avg_sq)):
+        assert th.equal(a, b)
+    # the next good step is the SECOND Adam step of every parameter, at the FOURTH scheduler step
+    ck_before = eng.checkpoint()
+    assert float(ck_before["optimizer_states"][0]["state"][0]["step"]) == 1.0
+    assert ck_before["lr_schedulers"][0]["last_epoch"] == 3
+    assert th.isfinite(eng.step(*good[2]))
+    assert not th.equal(snap[0], eng.flat.flat) and th.isfinite(eng.flat.flat).all()
+    # reference arithmetic of that step: torch Adam at step 2 with the lr of scheduler step 4
+    lr = eng.learning_rates(4)[0]
+    g = eng.grad[:1000].clone()
+    m = snap[1][:1000] + (g - snap[1][:1000]) * (1 - 0.9)
+    v = snap[2][:1000] * 0.999 + (1 - 0.999) * g * g
+    expect = snap[0][:1000] - (lr / (1 - 0.9 ** 2)) * (m / (v.sqrt() / (1 - 0.999 ** 2) ** 0.5 + 1e-5))
+    assert (eng.flat.flat[:1000] - expect).abs().max() < 1e-7
+
+
+def test_barf_training_loss_captured_matches_step_helper(cuda):
+    """BarfModel: the capturable device part (`training_loss` after `update_schedules`) equals the
+    reference-shaped `_step_helper` (loss, alpha, pose error), and an engine driving it through a CUDA
+    graph equals the eager engine."""
+    from nerf_experiments_b200 import model_interpolation_architecture as arch
+    from nerf_experiments_b200 import positional_encodings as pe
+    from nerf_experiments_b200 import scene
+    from nerf_experiments_b200.engine import TrainEngine
+    from nerf_experiments_b200.model_camera_calibration import BarfModel, LoopState
+
+    sc = scene.make_scene(6, 32, 32, cuda, rotation_noise=0.1, translation_noise=0.1, blur_sigmas=(4.0, 1.0, 0.0))
+    n_batches = 50
+
+    def build():
+        th.manual_seed(2)
+        ep = pe.BarfPositionalEncoding(10, 0.0, 0.2, 0.8, True, 1.0)
+        ed = pe.BarfPositionalEncoding(4, 0.0, 0.2, 0.8, True, 1.0)
+        net = arch.NerfModel(4, 256, True, False, 2, ep, ed, 5e-4, 1e-5, 1000)
+        m = BarfModel(n_training_images=6, camera_learning_rate_start=1e-3, camera_learning_rate_stop=1e-5,
+                      camera_learning_rate_decay_end=1000, near_sphere_normalized=2.0, far_sphere_normalized=8.0,
+                      model_radiance=net, samples_per_ray_radiance=32, max_gaussian_sigma=4.0,
+                      uniform_sampling_strategy="equidistant", uniform_sampling_offset_size=0.0).to(cuda)
+        m.loop = LoopState(sc.batcher, n_batches)
+        return m
+
+    g = th.Generator(device=cuda).manual_seed(0)
+    idx = th.randint(0, len(sc.batcher), (8, 128), device=cuda, generator=g)
+    batches = [sc.batcher.batch(idx[i]) for i in range(8)]
+
+    m = build()
+    step = 20                                  # epoch 0.4: mask partly open, blur level between two pyramid levels
+    m.update_schedules(step)
+    loss_dev, logs = m.training_loss(*batches[0])
+    loss_ref = m._step_helper(batches[0], step, "train")
+    assert float(loss_dev) == pytest.approx(float(loss_ref), rel=1e-6)
+    assert float(logs["pose_error"]) == pytest.approx(float(m._logged["pose_error"]), rel=1e-6)
+    assert float(logs["alpha"]) == pytest.approx(float(m._logged["alpha"]))
+
+    out = {}
+    for mode in ("eager", "graph"):
+        m = build()
+        eng = TrainEngine(m, cuda, loss_fn=m.training_loss)
+        losses = [float(eng.step(*batches[0]))]
+        if mode == "graph":
+            eng.capture(*batches[0])
+        for b in batches[1:]:
+            losses.append(float(eng.replay(*b) if mode == "graph" else eng.step(*b)))
+        out[mode] = (losses, eng.flat.flat.detach().clone(), float(eng.last_logs["pose_error"]))
+    assert out["eager"][0] == pytest.approx(out["graph"][0], rel=1e-4)
+    assert out["eager"][2] == pytest.approx(out["graph"][2], rel=1e-3)
+    diff = (out["eager"][1] - out["graph"][1]).abs()
+    assert float((diff > 2e-5).float().mean()) < 1e-3 and float(diff.max()) < 5e-3

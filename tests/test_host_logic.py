@@ -231,3 +231,32 @@ def test_sharded_render_assembles_the_rows_of_all_ranks(tmp_path):
     for p_ in procs:
         p_.join(timeout=60)
     assert results == [True, True]
+
+
+def test_exponential_lr_closed_form_matches_torch_scheduler():
+    """The fused Adam evaluates GARF's schedule in closed form on the device (engine.exponential_lr /
+    nerfb200_adam_step_dev); this pins the closed form to torch's ExponentialLR constructed the way
+    the reference constructs it (last_epoch = -decay_end - 1, garf/model_garf.py:365-428)."""
+    import math
+    import torch as th
+    from nerf_experiments_b200.engine import exponential_lr
+    lr0, stop, n = 5e-4, 5e-5, 7
+    gamma = 2 ** (math.log2(stop / lr0) / n)
+    p = th.nn.Parameter(th.zeros(1))
+    opt = th.optim.Adam([{"params": [p], "lr": lr0, "initial_lr": lr0}])
+    sched = th.optim.lr_scheduler.ExponentialLR(opt, gamma=gamma, last_epoch=-n - 1)
+    for step in range(1, 20):
+        assert opt.param_groups[0]["lr"] == pytest.approx(exponential_lr(lr0, math.log(gamma), n, step), rel=1e-9)
+        p.grad = th.ones(1)
+        opt.step()
+        sched.step()
+
+
+def test_le_nice_closed_form_edge_cases():
+    """lr = start * exp(logf * min(step, n)) with logf = 0 for the constant cases — including the
+    reference's n = -1 default of CameraExtrinsics, which evaluates to the STOP rate."""
+    from nerf_experiments_b200.model_interpolation import le_nice_lr, log_decay_factor
+    assert le_nice_lr(1e-3, log_decay_factor(1e-3, 1e-5, 0), 0, 5) == 1e-3
+    assert le_nice_lr(1e-3, log_decay_factor(1e-3, 1e-5, None), None, 5) == 1e-3
+    assert le_nice_lr(1e-3, log_decay_factor(1e-3, 1e-5, -1), -1, 5) == pytest.approx(1e-5)
+    assert le_nice_lr(1e-3, log_decay_factor(1e-3, 1e-5, 100), 100, 1000) == pytest.approx(1e-5)
