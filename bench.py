@@ -238,9 +238,9 @@ def run_ours(args):
     ms_e2e = float(t_e2e.item())
     h2d = sum(t.numel() * t.element_size() for t in host_batches[0])
 
+    eng.release_graph()          # before the process group goes: the graph holds the NCCL communicator
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        shutdown(world)
         return
 
     peaks = measured_peaks()
@@ -327,8 +327,21 @@ def run_ours(args):
         "clocks": clocks.summary(), "roofline": roofline, "cpu_baseline": cpu, "extras": extras,
     }
     emit_json(out)
-    if world > 1:
+    shutdown(world)
+
+
+def shutdown(world: int):
+    """Tears the process group down; never lets a stuck NCCL teardown hold the job (the result is out)."""
+    if world <= 1:
+        return
+    import torch.distributed as dist
+    timer = threading.Timer(20.0, lambda: os._exit(0))
+    timer.daemon = True
+    timer.start()
+    try:
         dist.destroy_process_group()
+    finally:
+        timer.cancel()
 
 
 # --------------------------------------------------------------------------------------------

@@ -20,7 +20,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
-#include "nerfb200_mlp.h" /* tile-program structs passed across the ABI */
+#include "nerfb200_mlp.h"  /* tile-program structs passed across the ABI */
+#include "nerfb200_garf.h" /* tile programs of the GARF networks */
 
 #ifdef __cplusplus
 extern "C" {
@@ -202,7 +203,40 @@ int nerfb200_mlp_bwd(const void* program_host, const void* wpack_t,
                      float* d_pos, float* d_dir, void* stream);
 int nerfb200_mlp_wgrad(const NbWgradItem* items_dev, int n_items, const void* x_stash,
                        int x_slabs_per_tile, const void* dy_stash, int dy_slabs_per_tile,
+                       const void* z_stash, int z_slabs_per_tile, const float* params,
                        float* d_params, void* stream);
+/* Sizes of the caller-owned workspaces of nerfb200_mlp_fwd (training) for n_samples samples:
+ * the activation stash and the ReLU sign-bit masks. (The dY stash of nerfb200_mlp_bwd is
+ * ceil(n / 128) * backward_program.stash_slabs_per_tile * 16384 bytes.) */
+int nerfb200_mlp_workspace_bytes(const void* program_host, long long n_samples,
+                                 long long* stash_bytes, long long* mask_bytes);
+
+/* ------------------------------------------------------------------------------------------
+ * a7, a8 (+ a6 inside). Fused GARF field: RadianceNetwork.forward (garf/model_radiance.py:84-96,
+ * == barf/model_garf_radiance.py:101-113) and ProposalNetwork.forward (garf/model_proposal.py:55-56)
+ * with the Gaussian activation (barf/gaussian.py:10-31) and their autograd, on per-ray or
+ * per-sample inputs (NbMlpInputs; positions o + t d are formed in registers, replacing
+ * GarfModel._get_positions / repeat_interleave, garf/model_garf.py:105,141). The tile programs
+ * (include/nerfb200_garf.h) come from the host mirror (nerf_experiments_b200/garf_program.py).
+ *   wpack / floats: packed bf16 weight images and fp32 values written by nerfb200_mlp_pack;
+ *   params: the flat fp32 master parameters (the first layer is evaluated from them in fp32);
+ *   fwd: out_sigma (N) [, out_rgb (N,3)]; y_stash / z_stash: NULL for inference, else workspaces of
+ *        nerfb200_garf_workspace_bytes() receiving the activations / pre-activations (bf16 slabs);
+ *   bwd: data gradients; dy_stash (backward_program.y_slabs_per_tile slabs per tile) receives dz of
+ *        every layer; parameter gradients come from nerfb200_mlp_wgrad over (y_stash, dy_stash,
+ *        z_stash): weight blocks as MMAs, bias and Gaussian-width gradients as column sums;
+ *        want_input_grads: also d(ray origin / direction) or d(position / direction) (+=).
+ */
+int nerfb200_garf_workspace_bytes(const void* program_host, long long n_samples,
+                                  long long* y_stash_bytes, long long* z_stash_bytes);
+int nerfb200_garf_fwd(const void* program_host, const void* wpack, const float* floats,
+                      const float* params, const NbMlpInputs* in_host, float* out_sigma,
+                      float* out_rgb, void* y_stash, void* z_stash, void* stream);
+int nerfb200_garf_bwd(const void* program_host, const void* wpack_t, const float* floats,
+                      const float* params, const NbMlpInputs* in_host, const float* sigma,
+                      const float* rgb, const float* g_sigma, const float* g_rgb,
+                      const void* z_stash, void* dy_stash, int want_input_grads, float* d_ray_o,
+                      float* d_ray_d, float* d_pos, float* d_dir, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * a6, a9. Learnable per-feature activations of the GARF / SARF / Gabor networks over (N, F)

@@ -148,11 +148,16 @@ typedef struct {
   int32_t reserved;
 } NbPackChunk;
 
-/* A packed bias segment: dst[dst_off + i] = params[base + i] for i < n, 0 for n <= i < n_padded */
+/* A packed fp32 segment: dst[dst_off + i] = f(params[base + i * stride]) for i < n, 0 for
+ * n <= i < n_padded; f = identity (NB_PACK_COPY) or the exponent coefficient of the Gaussian
+ * activation, -(s^2 + 1e-6) log2(e) (NB_PACK_GAUSS: y = exp2(z^2 * coefficient), barf/gaussian.py:10-19) */
+enum { NB_PACK_COPY = 0, NB_PACK_GAUSS = 1 };
 typedef struct {
   int64_t base;
   int32_t n, n_padded;
   int32_t dst_off;
+  int32_t kind;                 /* NB_PACK_*                                                   */
+  int32_t stride;               /* element stride in params (0 is read as 1)                   */
   int32_t reserved;
 } NbPackBias;
 
@@ -169,7 +174,14 @@ typedef struct {
   int32_t bias_dst;             /* float index of the bias gradient of output feature m0 (the */
                                 /* column sums of the dY slabs, += over the tile range), -1:  */
                                 /* another item of the same dY slabs carries it               */
+  int32_t mode;                 /* NB_WGRAD_MMA, or NB_WGRAD_COLSUM: no weight block — x_slab  */
+                                /* then indexes the Z stash (pre-activations of a Gaussian    */
+                                /* layer, n_x_slabs == n_dy_slabs) and the item reduces        */
+                                /* sum dz (bias) and sum z*dz (Gaussian width) per column      */
+  int32_t coef_dst;             /* COLSUM: float index of the inverse-std parameter (and of   */
+                                /* its gradient) of output feature m0, -1: none               */
 } NbWgradItem;
+enum { NB_WGRAD_MMA = 0, NB_WGRAD_COLSUM = 1 };
 
 #ifdef __cplusplus
 }

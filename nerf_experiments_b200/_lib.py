@@ -82,14 +82,61 @@ class NbPackChunk(C.Structure):
 
 class NbPackBias(C.Structure):
     _fields_ = [("base", C.c_int64), ("n", C.c_int32), ("n_padded", C.c_int32),
-                ("dst_off", C.c_int32), ("reserved", C.c_int32)]
+                ("dst_off", C.c_int32), ("kind", C.c_int32), ("stride", C.c_int32), ("reserved", C.c_int32)]
+
+    def __init__(self, *args, **kw):
+        kw.setdefault("kind", 0)
+        kw.setdefault("stride", 1)
+        kw.setdefault("reserved", 0)
+        super().__init__(*args, **kw)
+
+
+PACK_COPY, PACK_GAUSS = 0, 1
 
 
 class NbWgradItem(C.Structure):
     _fields_ = [("tile_begin", C.c_int32), ("tile_end", C.c_int32), ("n_dy_slabs", C.c_int32),
                 ("n_x_slabs", C.c_int32), ("dy_slab", C.c_int32), ("x_slab", C.c_int32),
                 ("m_real", C.c_int32), ("n_real", C.c_int32), ("dst", C.c_int64), ("ld", C.c_int32),
-                ("bias_dst", C.c_int32)]
+                ("bias_dst", C.c_int32), ("mode", C.c_int32), ("coef_dst", C.c_int32)]
+
+    def __init__(self, *args, **kw):
+        kw.setdefault("mode", 0)
+        kw.setdefault("coef_dst", -1)
+        super().__init__(*args, **kw)
+
+
+WGRAD_MMA, WGRAD_COLSUM = 0, 1
+
+# ---- mirrors of include/nerfb200_garf.h ------------------------------------------------------
+NG_MAX_OPS, NG_MAX_CHUNKS, NG_N_SLABS, NG_GEN_COLS, NG_MAX_FLOATS = 32, 6, 6, 128, 7680
+NG_STEP_NONE, NG_STEP_GEN, NG_STEP_ACT, NG_STEP_LINEAR, NG_STEP_RGB, NG_STEP_SIGMA = range(6)
+NG_BSTEP_HEAD, NG_BSTEP_ACT, NG_BSTEP_PLAIN = 8, 9, 10
+NG_F_SIGMA, NG_F_HOLD_SAVE, NG_F_HOLD_ADD, NG_F_DIRECT, NG_F_FIRST_LAYER = 1, 2, 4, 8, 16
+
+
+class NgStep(C.Structure):
+    _fields_ = [("kind", C.c_int8), ("wait_lag", C.c_int8), ("n_slabs", C.c_int8), ("out_slab", C.c_int8),
+                ("res_slab", C.c_int8), ("skip_src", C.c_int8), ("flags", C.c_int8), ("reserved", C.c_int8),
+                ("src_col", C.c_int16), ("sigma_col", C.c_int16), ("bias_off", C.c_int32), ("coef_off", C.c_int32),
+                ("skip_off", C.c_int32), ("y_stash", C.c_int32), ("z_stash", C.c_int32), ("gen_col0", C.c_int32)]
+
+
+class NgBlock(C.Structure):
+    _fields_ = [("tmem_col", C.c_int16), ("n", C.c_int16), ("row0", C.c_int16), ("reserved", C.c_int16)]
+
+
+class NgOp(C.Structure):
+    _fields_ = [("n_chunks", C.c_int8), ("n_blocks", C.c_int8), ("accumulate", C.c_int8), ("reserved", C.c_int8),
+                ("a_slab", C.c_int8 * NG_MAX_CHUNKS), ("k16", C.c_int8 * NG_MAX_CHUNKS), ("w_rows", C.c_int16),
+                ("reserved2", C.c_int16), ("w_off", C.c_int32 * NG_MAX_CHUNKS), ("blocks", NgBlock * 2)]
+
+
+class NgProgram(C.Structure):
+    _fields_ = [("n_ops", C.c_int32), ("y_slabs_per_tile", C.c_int32), ("z_slabs_per_tile", C.c_int32),
+                ("n_floats", C.c_int32), ("w1_off", C.c_int64), ("b1_off", C.c_int64), ("g1_off", C.c_int64),
+                ("n1", C.c_int32), ("aux_pos_stash", C.c_int32), ("aux_dir_stash", C.c_int32),
+                ("sigma_bias", C.c_float), ("ops", NgOp * NG_MAX_OPS), ("steps", NgStep * (NG_MAX_OPS + 1))]
 
 
 class NbAdamGroup(C.Structure):
@@ -149,7 +196,12 @@ def _declare(L):
                                     C.POINTER(NbPeCfg), vp, vp, f32, vp, vp, vp, vp, i32, i32, vp]
     L.nerfb200_mlp_bwd.argtypes = [vp, vp, C.POINTER(NbMlpInputs), C.POINTER(NbPeCfg), C.POINTER(NbPeCfg),
                                    vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, i32, i32, vp, vp, vp, vp, vp]
-    L.nerfb200_mlp_wgrad.argtypes = [vp, i32, vp, i32, vp, i32, vp, vp]
+    L.nerfb200_mlp_wgrad.argtypes = [vp, i32, vp, i32, vp, i32, vp, i32, vp, vp, vp]
+    L.nerfb200_mlp_workspace_bytes.argtypes = [vp, C.c_longlong, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+    L.nerfb200_garf_workspace_bytes.argtypes = [vp, C.c_longlong, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+    L.nerfb200_garf_fwd.argtypes = [vp, vp, vp, vp, C.POINTER(NbMlpInputs), vp, vp, vp, vp, vp]
+    L.nerfb200_garf_bwd.argtypes = [vp, vp, vp, vp, C.POINTER(NbMlpInputs), vp, vp, vp, vp, vp, vp, i32,
+                                    vp, vp, vp, vp, vp]
     L.nerfb200_adam_step.argtypes = [vp, vp, vp, vp, C.c_longlong, i32, vp, vp, vp, vp, f32, f32, f32,
                                      C.c_longlong, f32, vp]
     L.nerfb200_adam_step_dev.argtypes = [vp, vp, vp, vp, C.c_longlong, C.POINTER(NbAdamGroup), i32, f32, f32, f32,
@@ -174,6 +226,7 @@ EXPORTS = [
     "nerfb200_resample_alloc", "nerfb200_resample_fallback", "nerfb200_resample_icdf",
     "nerfb200_pose_fwd", "nerfb200_pose_bwd", "nerfb200_so3_to_SO3",
     "nerfb200_mlp_pack", "nerfb200_mlp_fwd", "nerfb200_mlp_fwd2", "nerfb200_mlp_bwd", "nerfb200_mlp_wgrad", "nerfb200_pe_fwd", "nerfb200_pe_bwd",
+    "nerfb200_mlp_workspace_bytes", "nerfb200_garf_workspace_bytes", "nerfb200_garf_fwd", "nerfb200_garf_bwd",
     "nerfb200_adam_step", "nerfb200_adam_step_dev", "nerfb200_act_fwd", "nerfb200_act_bwd", "nerfb200_ray_batch", "nerfb200_kabsch",
 ]
 

@@ -703,6 +703,16 @@ mlp_fwd2_kernel(const __grid_constant__ MlpFwd2Params pp) {
 
 using namespace nerfb200;
 
+extern "C" int nerfb200_mlp_workspace_bytes(const void* program_host, long long n_samples,
+                                            long long* stash_bytes, long long* mask_bytes) {
+  NB_CHECK_ARG(program_host && n_samples >= 0, "mlp_workspace_bytes: bad arguments");
+  const NbProgram* prog = reinterpret_cast<const NbProgram*>(program_host);
+  const long long n_tiles = (n_samples + NB_TILE_ROWS - 1) / NB_TILE_ROWS;
+  if (stash_bytes) *stash_bytes = n_tiles * prog->stash_slabs_per_tile * (long long)NB_SLAB_BYTES;
+  if (mask_bytes) *mask_bytes = n_tiles * prog->mask_words_per_tile * (long long)NB_TILE_ROWS * 4;
+  return NERFB200_OK;
+}
+
 extern "C" int nerfb200_debug_trace_fwd(long long* trace_dev) {
   NB_CHECK_CUDA(cudaMemcpyToSymbol(g_trace, &trace_dev, sizeof(trace_dev)));
   return NERFB200_OK;

@@ -47,8 +47,12 @@ mlp_pack_kernel(const float* __restrict__ params, const NbPackChunk* __restrict_
     }
   } else if (d - n_chunks < n_biases) {
     const NbPackBias b = biases[d - n_chunks];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < b.n_padded; i += gridDim.x * blockDim.x)
-      bias_out[b.dst_off + i] = (i < b.n) ? params[b.base + i] : 0.f;
+    const long long stride = b.stride > 0 ? b.stride : 1;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < b.n_padded; i += gridDim.x * blockDim.x) {
+      float v = (i < b.n) ? params[b.base + (long long)i * stride] : 0.f;
+      if (b.kind == NB_PACK_GAUSS && i < b.n) v = -(v * v + 1e-6f) * 1.4426950408889634f;
+      bias_out[b.dst_off + i] = v;
+    }
   }
 }
 

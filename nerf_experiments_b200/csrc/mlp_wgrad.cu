@@ -33,8 +33,10 @@ struct WgradParams {
   int* counter;                 // dynamic work distribution (zeroed by the host wrapper)
   const uint8_t* x_stash;
   const uint8_t* dy_stash;
-  int x_slabs_per_tile, dy_slabs_per_tile;
+  const uint8_t* z_stash;       // pre-activation stash of the GARF networks (column-sum items), may be NULL
+  int x_slabs_per_tile, dy_slabs_per_tile, z_slabs_per_tile;
   float* d_params;
+  const float* params;          // fp32 master parameters (Gaussian widths for their chain rule)
 };
 
 __global__ void __launch_bounds__(kWgThreads, 1)
@@ -73,7 +75,9 @@ mlp_wgrad_kernel(const __grid_constant__ WgradParams p) {
         const uint32_t bytes = (uint32_t)(item.n_dy_slabs + item.n_x_slabs) * kHalfSlabBytes;
         for (int tile = item.tile_begin; tile < item.tile_end; ++tile) {
           const uint8_t* dy = p.dy_stash + ((size_t)tile * p.dy_slabs_per_tile + item.dy_slab) * NB_SLAB_BYTES;
-          const uint8_t* x = p.x_stash + ((size_t)tile * p.x_slabs_per_tile + item.x_slab) * NB_SLAB_BYTES;
+          const uint8_t* x = item.mode == NB_WGRAD_COLSUM
+              ? p.z_stash + ((size_t)tile * p.z_slabs_per_tile + item.x_slab) * NB_SLAB_BYTES
+              : p.x_stash + ((size_t)tile * p.x_slabs_per_tile + item.x_slab) * NB_SLAB_BYTES;
           for (int half = 0; half < 2; ++half) {
             mbar_wait(&empty[stage], phase ^ 1u);
             mbar_arrive_expect_tx(&full[stage], bytes);
@@ -92,17 +96,28 @@ mlp_wgrad_kernel(const __grid_constant__ WgradParams p) {
   } else if (warp == 4) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, e_phase = 0;
-      bool first_item = true;
+      bool flush_pending = false;
       for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
         const NbWgradItem item = p.items[it];
+        if (item.mode == NB_WGRAD_COLSUM) {
+          // column-sum item: no MMA — the stages only pass through the four summing warps
+          for (int tile = item.tile_begin; tile < item.tile_end; ++tile) {
+            for (int half = 0; half < 2; ++half) {
+              mbar_wait(&full[stage], phase);
+              mbar_arrive(&empty[stage]);
+              if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
+            }
+          }
+          continue;
+        }
         const int n_mb = (item.n_dy_slabs + 1) / 2;
         const uint32_t idesc = umma_idesc(128, item.n_x_slabs * 64, true, true);
-        if (!first_item) {   // the flush of the previous item must have drained TMEM
+        if (flush_pending) {   // the flush of the previous MMA item must have drained TMEM
           mbar_wait(acc_empty, e_phase);
           e_phase ^= 1u;
           tcgen05_fence_after();
         }
-        first_item = false;
+        flush_pending = true;
         uint32_t acc = 0;
         for (int tile = item.tile_begin; tile < item.tile_end; ++tile) {
           for (int half = 0; half < 2; ++half) {
@@ -133,12 +148,13 @@ mlp_wgrad_kernel(const __grid_constant__ WgradParams p) {
     for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
       const NbWgradItem item = p.items[it];
       const int n_mb = (item.n_dy_slabs + 1) / 2;
-      const bool sums = item.bias_dst >= 0 && warp < item.n_dy_slabs;
-      float bacc[8][8];
+      const bool colsum = item.mode == NB_WGRAD_COLSUM;
+      const bool sums = (item.bias_dst >= 0 || (colsum && item.coef_dst >= 0)) && warp < item.n_dy_slabs;
+      float bacc[8][8], zacc[8][8];
 #pragma unroll
       for (int q = 0; q < 8; ++q)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) bacc[q][e] = 0.f;
+        for (int e = 0; e < 8; ++e) { bacc[q][e] = 0.f; zacc[q][e] = 0.f; }
       for (int tile = item.tile_begin; tile < item.tile_end; ++tile) {
         for (int half = 0; half < 2; ++half) {
           mbar_wait(&full[stage], phase);
@@ -154,6 +170,17 @@ mlp_wgrad_kernel(const __grid_constant__ WgradParams p) {
                 bacc[q][2] += __uint_as_float(v.y << 16); bacc[q][3] += __uint_as_float(v.y & 0xffff0000u);
                 bacc[q][4] += __uint_as_float(v.z << 16); bacc[q][5] += __uint_as_float(v.z & 0xffff0000u);
                 bacc[q][6] += __uint_as_float(v.w << 16); bacc[q][7] += __uint_as_float(v.w & 0xffff0000u);
+                if (colsum) {   // Gaussian width gradient: sum over samples of z * dz (same slab position in the z stash)
+                  const uint4 z = *reinterpret_cast<const uint4*>(base + 4u * kHalfSlabBytes + (uint32_t)(r8 * 8 + q) * 128u);
+                  zacc[q][0] = fmaf(__uint_as_float(z.x << 16), __uint_as_float(v.x << 16), zacc[q][0]);
+                  zacc[q][1] = fmaf(__uint_as_float(z.x & 0xffff0000u), __uint_as_float(v.x & 0xffff0000u), zacc[q][1]);
+                  zacc[q][2] = fmaf(__uint_as_float(z.y << 16), __uint_as_float(v.y << 16), zacc[q][2]);
+                  zacc[q][3] = fmaf(__uint_as_float(z.y & 0xffff0000u), __uint_as_float(v.y & 0xffff0000u), zacc[q][3]);
+                  zacc[q][4] = fmaf(__uint_as_float(z.z << 16), __uint_as_float(v.z << 16), zacc[q][4]);
+                  zacc[q][5] = fmaf(__uint_as_float(z.z & 0xffff0000u), __uint_as_float(v.z & 0xffff0000u), zacc[q][5]);
+                  zacc[q][6] = fmaf(__uint_as_float(z.w << 16), __uint_as_float(v.w << 16), zacc[q][6]);
+                  zacc[q][7] = fmaf(__uint_as_float(z.w & 0xffff0000u), __uint_as_float(v.w & 0xffff0000u), zacc[q][7]);
+                }
               }
             }
           }
@@ -177,14 +204,40 @@ mlp_wgrad_kernel(const __grid_constant__ WgradParams p) {
           tot[e] += __shfl_xor_sync(0xffffffffu, tot[e], 8);
           tot[e] += __shfl_xor_sync(0xffffffffu, tot[e], 16);
         }
-        if (rg == 0 && item.tile_end > item.tile_begin) {
+        if (rg == 0 && item.tile_end > item.tile_begin && item.bias_dst >= 0) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int m = warp * 64 + pc * 8 + e;
             if (m < item.m_real) atomicAdd(p.d_params + item.bias_dst + m, tot[e]);
           }
         }
+        if (colsum && item.coef_dst >= 0) {
+          float zt[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) zt[e] = zacc[0][e];
+#pragma unroll
+          for (int q = 1; q < 8; ++q)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) zt[e] += __shfl_xor_sync(0xffffffffu, zacc[q][e], q);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            zt[e] += __shfl_xor_sync(0xffffffffu, zt[e], 8);
+            zt[e] += __shfl_xor_sync(0xffffffffu, zt[e], 16);
+          }
+          if (rg == 0 && item.tile_end > item.tile_begin) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int m = warp * 64 + pc * 8 + e;
+              if (m < item.m_real) {
+                // y = exp(-z^2 v), v = s^2 + 1e-6: dL/ds = 2 s dL/dv, dL/dv = sum z dz / (2 v)
+                const float sdev = __ldg(p.params + item.coef_dst + m);
+                atomicAdd(p.d_params + item.coef_dst + m, zt[e] * sdev / (sdev * sdev + 1e-6f));
+              }
+            }
+          }
+        }
       }
+      if (colsum) continue;
       mbar_wait(acc_full, f_phase);
       f_phase ^= 1u;
       tcgen05_fence_after();
@@ -234,7 +287,8 @@ using namespace nerfb200;
 
 extern "C" int nerfb200_mlp_wgrad(const NbWgradItem* items_dev, int n_items, const void* x_stash,
                                   int x_slabs_per_tile, const void* dy_stash,
-                                  int dy_slabs_per_tile, float* d_params, void* stream) {
+                                  int dy_slabs_per_tile, const void* z_stash, int z_slabs_per_tile,
+                                  const float* params, float* d_params, void* stream) {
   NB_CHECK_ARG(n_items >= 0 && (n_items == 0 || (items_dev && x_stash && dy_stash && d_params)),
                "mlp_wgrad: bad arguments");
   if (n_items == 0) return NERFB200_OK;
@@ -244,9 +298,12 @@ extern "C" int nerfb200_mlp_wgrad(const NbWgradItem* items_dev, int n_items, con
   p.counter = nullptr;
   p.x_stash = reinterpret_cast<const uint8_t*>(x_stash);
   p.dy_stash = reinterpret_cast<const uint8_t*>(dy_stash);
+  p.z_stash = reinterpret_cast<const uint8_t*>(z_stash);
   p.x_slabs_per_tile = x_slabs_per_tile;
   p.dy_slabs_per_tile = dy_slabs_per_tile;
+  p.z_slabs_per_tile = z_slabs_per_tile;
   p.d_params = d_params;
+  p.params = params;
   static bool configured = false;
   if (!configured) {
     NB_CHECK_CUDA(cudaFuncSetAttribute(mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

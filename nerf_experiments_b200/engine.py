@@ -229,6 +229,18 @@ class TrainEngine:
         self.flat.version += 1
         return self
 
+    def release_graph(self):
+        """Drops the captured graph. A graph that contains NCCL collectives keeps the communicator busy:
+        `torch.distributed.destroy_process_group()` blocks (observed on 2 x B200, torch 2.11 / NCCL 2.28)
+        until every such graph has been destroyed — call this before tearing the process group down."""
+        if self._graph is not None:
+            th.cuda.synchronize(self.device)
+            self._graph = None
+            self._static_logs = None
+            import gc
+            gc.collect()
+            th.cuda.synchronize(self.device)
+
     def replay(self, *batch):
         """One captured step on a new batch (same shapes as at capture); returns the (fine) loss tensor,
         which the NEXT replay overwrites (as all of `last_logs`)."""

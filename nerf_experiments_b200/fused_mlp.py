@@ -252,7 +252,7 @@ class FusedField:
             items_dev, n_items = self._items(n_tiles)
             self._timed("mlp_wgrad", lambda: check(lib().nerfb200_mlp_wgrad(
                 _ptr(items_dev), n_items, _ptr(stash), cm.stash_slabs_per_tile, _ptr(dy_stash),
-                cb.dy_slabs_per_tile, _ptr(flat_grad), stream), "mlp_wgrad"))
+                cb.dy_slabs_per_tile, None, 0, _ptr(self.flat.flat), _ptr(flat_grad), stream), "mlp_wgrad"))
         return flat_grad, d_a, d_b
 
 

@@ -295,6 +295,8 @@ class WgradUnit:
     dst: int
     ld: int
     bias_dst: int = -1     # float index of the bias gradient of the unit's first output feature
+    mode: int = 0          # _lib.WGRAD_MMA | _lib.WGRAD_COLSUM (x_slab then indexes the z stash)
+    coef_dst: int = -1     # COLSUM: float index of the Gaussian inverse-std parameter of the first feature
 
 
 @dataclass
@@ -501,6 +503,6 @@ def schedule_wgrad(units: List[WgradUnit], n_tiles: int, n_workers: int):
                 items.append((c * (t1 - t0), NbWgradItem(tile_begin=t0, tile_end=t1, n_dy_slabs=u.n_dy_slabs,
                                                          n_x_slabs=u.n_x_slabs, dy_slab=u.dy_slab, x_slab=u.x_slab,
                                                          m_real=u.m_real, n_real=u.n_real, dst=u.dst, ld=u.ld,
-                                                         bias_dst=u.bias_dst)))
+                                                         bias_dst=u.bias_dst, mode=u.mode, coef_dst=u.coef_dst)))
     items.sort(key=lambda t: -t[0])
     return [it for _, it in items]

@@ -44,9 +44,10 @@ def test_struct_sizes_match_the_header():
     from nerf_experiments_b200 import _lib
     src = r'''
 #include <stdio.h>
-#include "nerfb200_mlp.h"
-int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(NbBlock), sizeof(NbOp), sizeof(NbProgram),
-  sizeof(NbPeCfg), sizeof(NbMlpInputs), sizeof(NbPackChunk), sizeof(NbPackBias), sizeof(NbWgradItem)); return 0; }
+#include "nerfb200.h"
+int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(NbBlock), sizeof(NbOp), sizeof(NbProgram),
+  sizeof(NbPeCfg), sizeof(NbMlpInputs), sizeof(NbPackChunk), sizeof(NbPackBias), sizeof(NbWgradItem),
+  sizeof(NgStep), sizeof(NgBlock), sizeof(NgOp), sizeof(NgProgram), sizeof(NbAdamGroup)); return 0; }
 '''
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "s.c")
@@ -55,7 +56,7 @@ int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(NbBlock), si
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
     mirrors = [_lib.NbBlock, _lib.NbOp, _lib.NbProgram, _lib.NbPeCfg, _lib.NbMlpInputs, _lib.NbPackChunk,
-               _lib.NbPackBias, _lib.NbWgradItem]
+               _lib.NbPackBias, _lib.NbWgradItem, _lib.NgStep, _lib.NgBlock, _lib.NgOp, _lib.NgProgram, _lib.NbAdamGroup]
     assert sizes == [ctypes.sizeof(m) for m in mirrors]
 
 

@@ -20,9 +20,11 @@ def _build_and_batches(dev, n_steps, B):
 
 
 def _rank_main(rank, world, init_file, out_file, n_steps, B):
+    import faulthandler
     import torch.distributed as dist
     from nerf_experiments_b200.engine import TrainEngine
     from nerf_experiments_b200.parallel import shard_range
+    faulthandler.dump_traceback_later(90, exit=True)      # a hang becomes a stack dump and a failure
     dev = th.device("cuda", rank)
     th.cuda.set_device(dev)
     dist.init_process_group("nccl", init_method=f"file://{init_file}", rank=rank, world_size=world, device_id=dev)
@@ -45,6 +47,7 @@ def _rank_main(rank, world, init_file, out_file, n_steps, B):
     if rank == 0:
         th.save({"flat": eng.flat.flat.cpu(), "flat_other": flat_all[1].cpu(), "losses": (mean_losses / world).cpu(),
                  "steps": eng.state[:2].tolist()}, out_file)
+    eng.release_graph()            # a graph holding NCCL collectives would block the teardown
     dist.barrier()
     dist.destroy_process_group()
 
