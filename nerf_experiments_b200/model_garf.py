@@ -123,10 +123,9 @@ class GarfModel(LightningModule):
         s_edges = ops.resample_icdf(s_edges, cdf, self.proposal_samples_per_ray, u_prop)
         t = self._s_to_t(s_edges)
         t0, t1 = t[:, :-1].contiguous(), t[:, 1:].contiguous()
-        with th.set_grad_enabled(th.is_grad_enabled()):
-            pos = self._get_positions(ray_origs, ray_dirs, t0, t1)
-            sigma = self.proposal_network(pos.view(-1, 3)).view(t0.shape)
-            _, cdf = transmittance_cdf(sigma, t0, t1)
+        # the closure of garf/model_garf.py:127-141 (positions, network) as one fused launch on the rays
+        sigma = self.proposal_network.forward_rays(ray_origs, ray_dirs, t0, t1)
+        _, cdf = transmittance_cdf(sigma, t0, t1)
         self._prop_cache = (t, cdf)
         # radiance level
         s_edges = ops.resample_icdf(s_edges, cdf.detach(), self.radiance_samples_per_ray, u_rad)
@@ -136,10 +135,7 @@ class GarfModel(LightningModule):
     # -- forward -----------------------------------------------------------------------------
     def forward(self, ray_origs: th.Tensor, ray_dirs: th.Tensor, u_rays=None):
         t_starts, t_ends = self._sampling(ray_origs, ray_dirs, u_rays)
-        S = t_starts.shape[1]
-        pos = self._get_positions(ray_origs, ray_dirs, t_starts, t_ends)
-        rgb_s, sigma = self.radiance_network(pos.view(-1, 3), ray_dirs.repeat_interleave(S, dim=0))
-        rgb_s, sigma = rgb_s.view(-1, S, 3), sigma.view(-1, S)
+        rgb_s, sigma = self.radiance_network.forward_rays(ray_origs, ray_dirs, t_starts, t_ends)
         rgb, weights, opacity, depth = _CompositeNerfacc.apply(sigma, rgb_s, t_starts, t_ends)
         with th.no_grad():
             trans, _ = transmittance_cdf(sigma, t_starts, t_ends)

@@ -3,20 +3,20 @@
 `model_density_1.{0..7}`, `model_density_2.{0..6}`, `model_color.{0..3}`), seeded initialisation,
 `parameters_linear()` / `parameters_gaussian()` and `forward(pos, dir) -> (rgb, density)`.
 
-Round-1 status: the Gaussian activations (forward, input / parameter / bias gradients) run in the
-CUDA kernels of csrc/activations.cu; the Linear layers are plain library GEMMs (cuBLAS through
-torch) on the tensor cores with TF32 operands — the precision class the reference trains at
-(`matmul_precision = "fp32"` restores fp32 GEMMs, `"bf16"` runs bf16 operands with bf16
-activations between the layers). The layers are up to 1024 wide, which
-does not fit the 256-column tile program of the fused kernel: fusing this network
-is the round-2 item. th.compile of the reference is dropped (no tracing compiler)."""
+The whole network (11 Linear layers, 8 Gaussian activations, the residual and the two raw-xyz /
+direction concatenations) runs as ONE fused kernel per pass on a 128-sample tile that stays on the
+SM — csrc/garf_fwd.cu, garf_bwd.cu, mlp_wgrad.cu; tile program from garf_program.py. No library GEMM
+and no CPU path: a CPU tensor raises. th.compile of the reference is dropped (no tracing compiler)."""
 from typing import Iterator
 
 import torch as th
 import torch.nn as nn
 
-from . import _lib, ops
+from .fused_garf import FusedGarfField, garf_rays, garf_samples
+from .fused_mlp import FlatParams
+from .garf_program import GaussLinear, compile_proposal, compile_radiance
 from .gaussian import GaussAct
+from .mlp_program import Linear
 
 
 class _GaussNetBase(nn.Module):
@@ -26,32 +26,8 @@ class _GaussNetBase(nn.Module):
         self.gaussian_init_max = gaussian_init_max
         self._parameters_linear: list = []
         self._parameters_gaussian: list = []
-        # GEMM arithmetic: "tf32" (default: fp32 tensors, TF32 tensor-core GEMMs), "bf16" (bf16 operands,
-        # fp32 accumulation and pre-activations, bf16 activations between the layers: measured SLOWER
-        # with cuBLAS, whose bf16-in / fp32-out GEMMs fall back to pre-Blackwell kernels) or "fp32"
-        self.matmul_precision = "tf32"
-
-    def _run(self, seq: nn.Sequential, x: th.Tensor) -> th.Tensor:
-        """seq(x) with every Linear (+ GaussAct) pair as one fused-gradient op; fp32 in, fp32 out."""
-        mods = list(seq)
-        n_lin = sum(isinstance(m, nn.Linear) for m in mods)
-        i = seen = 0
-        while i < len(mods):
-            m = mods[i]
-            if isinstance(m, nn.Linear) and x.is_cuda:
-                seen += 1
-                last = seen == n_lin
-                nxt = mods[i + 1] if i + 1 < len(mods) else None
-                if isinstance(nxt, GaussAct):
-                    x = ops.linear_activation(x, m.weight, m.bias, _lib.ACT_GAUSS, nxt.inv_standard_deviation,
-                                              None, self.matmul_precision, last)
-                    i += 2
-                    continue
-                x = ops.linear_activation(x, m.weight, m.bias, -1, None, None, self.matmul_precision, last)
-            else:
-                x = m(x.float() if x.dtype == th.bfloat16 else x)
-            i += 1
-        return x.float() if x.dtype == th.bfloat16 else x
+        self._flat = None
+        self._field = None
 
     def _create_linear(self, features_in: int, features_out: int) -> nn.Linear:
         linear = nn.Linear(features_in, features_out)
@@ -69,6 +45,32 @@ class _GaussNetBase(nn.Module):
 
     def parameters_gaussian(self) -> Iterator[nn.Parameter]:
         return iter(self._parameters_gaussian)
+
+    # ---- fused field -----------------------------------------------------------------------------
+    def _gauss_linears(self, fp: FlatParams, seqs):
+        """[GaussLinear] of every Linear of the given Sequentials, in order (a GaussAct behind a Linear is
+        its activation)."""
+        out = []
+        for seq in seqs:
+            mods = list(seq)
+            for i, m in enumerate(mods):
+                if isinstance(m, nn.Linear):
+                    nxt = mods[i + 1] if i + 1 < len(mods) else None
+                    g = fp.offset_of(nxt.inv_standard_deviation) if isinstance(nxt, GaussAct) else -1
+                    out.append(GaussLinear(Linear(fp.offset_of(m.weight), fp.offset_of(m.bias), m.out_features,
+                                                  m.in_features), g))
+        return out
+
+    def _compile(self, fp: FlatParams):
+        raise NotImplementedError
+
+    def fused_field(self, flat: FlatParams = None) -> FusedGarfField:
+        """The compiled fused field of this network; `flat` lets a caller (engine.TrainEngine) place the
+        parameters of several networks in one shared flat buffer."""
+        if self._field is None or (flat is not None and flat is not self._flat):
+            self._flat = flat if flat is not None else FlatParams(list(self.parameters()))
+            self._field = FusedGarfField(self._compile, self._flat, own_params=list(self.parameters()))
+        return self._field
 
 
 class RadianceNetwork(_GaussNetBase):
@@ -90,9 +92,17 @@ class RadianceNetwork(_GaussNetBase):
             self._create_linear(128 + 3, 256), self._create_gaussian(256),
             self._create_linear(256, 3), nn.Sigmoid())
 
+    def _compile(self, fp: FlatParams):
+        layers = self._gauss_linears(fp, (self.model_density_1, self.model_density_2, self.model_color))
+        return compile_radiance(layers[:8], layers[8:])
+
     def forward(self, pos: th.Tensor, dir: th.Tensor):
-        z1 = self._run(self.model_density_1, pos)
-        z2 = self._run(self.model_density_2, th.cat((z1, pos), dim=1))
-        density = self.softplus(z2[:, 128] - 1)
-        rgb = self._run(self.model_color, th.cat((z1[:, :128] + z2[:, :128], dir), dim=1))
+        """(rgb (N,3), density (N,)) for per-sample positions / directions (garf/model_radiance.py:84-96)."""
+        density, rgb = garf_samples(self, pos, dir)
+        return rgb, density
+
+    def forward_rays(self, ray_origs: th.Tensor, ray_dirs: th.Tensor, t_starts: th.Tensor, t_ends: th.Tensor):
+        """(rgb (B,S,3), density (B,S)) at the mid-points of the bins: GarfModel._get_positions +
+        repeat_interleave + forward (garf/model_garf.py:105,163-188) without materialising positions."""
+        density, rgb = garf_rays(self, ray_origs, ray_dirs, t_starts, t_ends)
         return rgb, density

@@ -69,44 +69,123 @@ def _seeded_nets(cuda):
     return prop.to(cuda), rad.to(cuda)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
-def test_garf_networks_match_reference(cuda, precision):
-    """Against the reference modules' fp32 outputs / gradients.  fp32 GEMMs: element-wise tight.  TF32 (the
-    default; the reference's own matmul precision class) and bf16 operands: rgb well inside the north-star
-    1e-2 and every parameter gradient within a small relative L2 error (measured on B200: TF32 rgb 1e-4,
-    gradients <= 1.2e-3; bf16 rgb 7e-4, gradients <= 1e-2 — scripts/garf_precision.py)."""
+def _rel(a, b):
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+def test_garf_networks_match_reference(cuda):
+    """The fused GARF kernels against the outputs / gradients of the UNMODIFIED reference modules
+    (tests/golden/garf.npz, fp32). Arithmetic of the fused path: fp32 first layer and raw-coordinate
+    terms, bf16 operands with fp32 accumulation elsewhere, bf16 stashes. Stated tolerances: rgb 1e-2
+    absolute (north_star's bf16-MLP bound), density 2 % of its range, every parameter gradient 4 %
+    relative L2 (measured on B200: see the assertion messages / profiles)."""
     g = _g()
     prop, rad = _seeded_nets(cuda)
-    prop.matmul_precision = rad.matmul_precision = precision
-    out_atol, out_rtol, grad_rel = {"fp32": (1e-5, 1e-4, None), "tf32": (1e-3, 2e-3, 5e-3), "bf16": (5e-3, 1e-2, 3e-2)}[precision]
 
     def check_grads(net, prefix):
+        worst = 0.0
         for n, p in net.named_parameters():
             ref = g[prefix + n]
             got = _thin(p.grad).cpu()
-            if grad_rel is None:
-                assert th.allclose(got, ref, rtol=5e-3, atol=2e-5 * float(ref.abs().max() + 1)), n
-            else:
-                assert float((got - ref).norm()) <= grad_rel * float(ref.norm()) + 1e-7, n
+            err = _rel(got, ref)
+            worst = max(worst, err)
+            assert err < 4e-2, (n, err)
+        return worst
 
-    rgb, dens = rad(g["net_pos"].to(cuda), g["net_dir"].to(cuda))
-    assert th.allclose(rgb.cpu(), g["rad_rgb"], rtol=out_rtol, atol=out_atol)
-    assert th.allclose(dens.cpu(), g["rad_density"], rtol=out_rtol, atol=out_atol)
+    pos, dirs = g["net_pos"].to(cuda), g["net_dir"].to(cuda)
+    rgb, dens = rad(pos, dirs)
+    assert (rgb.cpu() - g["rad_rgb"]).abs().max() < 1e-2
+    assert (dens.cpu() - g["rad_density"]).abs().max() < 2e-2 * (1 + g["rad_density"].abs().max())
     ((rgb * g["up_rgb"].to(cuda)).sum() + (dens * g["up_density"].to(cuda)).sum()).backward()
-    check_grads(rad, "rad.grad.")
-    sp = prop(g["net_pos"].to(cuda))
-    assert th.allclose(sp.cpu(), g["prop_sigma"], rtol=out_rtol, atol=out_atol)
+    w_rad = check_grads(rad, "rad.grad.")
+    sp = prop(pos)
+    assert sp.shape == (pos.shape[0], 1)
+    assert (sp.cpu() - g["prop_sigma"]).abs().max() < 2e-2 * (1 + g["prop_sigma"].abs().max())
     (sp * g["up_prop"].to(cuda)).sum().backward()
-    check_grads(prop, "prop.grad.")
+    w_prop = check_grads(prop, "prop.grad.")
+    print(f"worst relative L2 gradient error: radiance {w_rad:.3e}, proposal {w_prop:.3e}")
+
+
+@pytest.mark.parametrize("N", [1, 127, 128, 300, 5000])
+def test_garf_kernels_match_the_program_interpreter(cuda, N):
+    """The CUDA kernels against the CPU interpreter of the same tile programs (tests/garf_sim.py: same
+    roundings), ragged sizes included: outputs to 2e-3, parameter and input gradients to 1.5 % relative
+    L2 (summation order and exp2 approximations are what is left)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import garf_sim
+    prop, rad = _seeded_nets(cuda)
+    gen = th.Generator().manual_seed(N)
+    pos = th.randn((N, 3), generator=gen) * 1.2
+    dirs = th.nn.functional.normalize(th.randn((N, 3), generator=gen), dim=1)
+    up_s, up_c = th.randn(N, generator=gen), th.randn((N, 3), generator=gen)
+    for net, has_dir in ((rad, True), (prop, False)):
+        f = net.fused_field()
+        f.prepare(cuda)
+        flat = f.flat.flat.detach().cpu()
+        pc = pos.to(cuda).requires_grad_()
+        dc = dirs.to(cuda).requires_grad_()
+        if has_dir:
+            rgb, dens = net(pc, dc)
+            loss = (rgb * up_c.to(cuda)).sum() + (dens * up_s.to(cuda)).sum()
+        else:
+            dens = net(pc)[:, 0]
+            rgb = None
+            loss = (dens * up_s.to(cuda)).sum()
+        loss.backward()
+        s_sigma, s_rgb, s_grad, s_dpos, s_ddir = garf_sim.run_network(f.compiled, flat, pos, dirs if has_dir else None,
+                                                                    up_s, up_c if has_dir else None)
+        assert (dens.detach().cpu() - s_sigma).abs().max() < 2e-3 * (1 + s_sigma.abs().max())
+        if has_dir:
+            assert (rgb.detach().cpu() - s_rgb).abs().max() < 2e-3
+        for p in net.parameters():
+            o = f.flat.offset_of(p)
+            ref = s_grad[o: o + p.numel()].view(p.shape)
+            assert _rel(p.grad.cpu(), ref) < 1.5e-2 or float((p.grad.cpu() - ref).abs().max()) < 1e-6, (has_dir, tuple(p.shape))
+        assert _rel(pc.grad.cpu(), s_dpos) < 1.5e-2
+        if has_dir:
+            assert _rel(dc.grad.cpu(), s_ddir) < 1.5e-2
+
+
+def test_garf_rays_mode_equals_samples_mode(cuda):
+    """forward_rays (positions o + (t0 + t1) / 2 d formed in registers) == forward on materialised
+    positions (GarfModel._get_positions, garf/model_garf.py:105), values and ray gradients."""
+    prop, rad = _seeded_nets(cuda)
+    B, S = 37, 20
+    gen = th.Generator().manual_seed(9)
+    o = (th.nn.functional.normalize(th.randn((B, 3), generator=gen), dim=1) * 4.0).to(cuda).requires_grad_()
+    d = th.nn.functional.normalize(-o.detach().cpu() + 0.3 * th.randn((B, 3), generator=gen), dim=1).to(cuda).requires_grad_()
+    t = th.sort(th.rand((B, S + 1), generator=gen) * 5 + 2, dim=1).values.to(cuda)
+    t0, t1 = t[:, :-1].contiguous(), t[:, 1:].contiguous()
+    up = th.randn((B, S, 3), generator=gen).to(cuda)
+    rgb_r, dens_r = rad.forward_rays(o, d, t0, t1)
+    ((rgb_r * up).sum() + dens_r.sum()).backward()
+    go_r, gd_r = o.grad.clone(), d.grad.clone()
+    gw_r = rad.model_density_1[2].weight.grad.clone()
+    o.grad = d.grad = None
+    rad.zero_grad()
+    pos = o[:, None] + d[:, None] * (t0 + t1)[..., None] / 2
+    rgb_s, dens_s = rad(pos.view(-1, 3), d.repeat_interleave(S, dim=0))
+    ((rgb_s.view(B, S, 3) * up).sum() + dens_s.sum()).backward()
+    assert th.equal(rgb_r.reshape(-1, 3), rgb_s) and th.equal(dens_r.reshape(-1), dens_s)
+    assert _rel(go_r, o.grad) < 1e-4 and _rel(gd_r, d.grad) < 1e-4
+    assert _rel(gw_r, rad.model_density_1[2].weight.grad) < 1e-4
+    sp = prop.forward_rays(o, d, t0, t1)
+    assert th.equal(sp.reshape(-1, 1), prop(pos.view(-1, 3).detach()))
+
+
+def test_garf_networks_refuse_cpu_tensors():
+    from nerf_experiments_b200.model_garf_radiance import RadianceNetwork
+    net = RadianceNetwork(0.5, 1.5)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(th.zeros(4, 3), th.zeros(4, 3))
 
 
 @pytest.mark.parametrize("training", [True, False])
 def test_garf_model_chain_matches_oracle(cuda, training):
     from nerf_experiments_b200.model_garf import GarfModel
-    th.backends.cuda.matmul.allow_tf32 = False
     th.manual_seed(3)
     m = GarfModel(2.0, 7.0, 32, 48, 0.5, 1.5, 1.0, 1e-3, 1e-4, 100, 0.0, 1e-3, 1e-4, 100, 0.0).to(cuda)
-    m.proposal_network.matmul_precision = m.radiance_network.matmul_precision = "fp32"   # tight comparison
     m.train(training)
     B = 24
     gen = th.Generator().manual_seed(11)
@@ -121,23 +200,22 @@ def test_garf_model_chain_matches_oracle(cuda, training):
     uc = None if u is None else (u[0].to(cuda), u[1].to(cuda))
     rgb, (lp, lr) = m._forward_loss((o.to(cuda), d.to(cuda), target.to(cuda)), uc)
     _, opacity, depth, extras = m(o.to(cuda), d.to(cuda), uc)
-    # the sample intervals follow from bit-exact inverse-CDF resampling of a cdf that is itself
-    # the output of fp32 GEMMs: equal to a few ulp of t
-    assert th.allclose(extras["t_starts"].cpu(), r0, rtol=0, atol=2e-4)
-    assert th.allclose(rgb.cpu(), r_rgb, atol=2e-4)
-    assert th.allclose(opacity[:, 0].cpu(), r_op, atol=2e-4)
-    assert th.allclose(depth[:, 0].cpu(), r_dp, atol=2e-3)
-    assert float(lp) == pytest.approx(float(r_lp), rel=2e-2, abs=1e-7)
+    # The oracle runs the networks in fp32, the fused kernels with bf16 operands: the proposal densities
+    # differ by ~1 %, so the resampled intervals (a continuous function of the proposal cdf) move by a
+    # fraction of a bin, and everything downstream inherits that. Stated bounds:
+    assert th.allclose(extras["t_starts"].cpu(), r0, rtol=0, atol=3e-2)
+    assert th.allclose(rgb.cpu(), r_rgb, atol=1e-2)                      # north_star: bf16-MLP rgb 1e-2 abs
+    assert th.allclose(opacity[:, 0].cpu(), r_op, atol=1e-2)
+    assert th.allclose(depth[:, 0].cpu(), r_dp, atol=5e-2)
+    assert float(lp) == pytest.approx(float(r_lp), rel=0.15, abs=1e-6)
     # gradients of the summed loss reach both networks like in the reference's manual optimisation
     (lp + lr).backward()
     r_loss = r_lp + th.nn.functional.mse_loss(r_rgb, target)
     r_loss.backward()
     for n, p in m.radiance_network.named_parameters():
-        ref = sd_r[n].grad
-        assert th.allclose(p.grad.cpu(), ref, rtol=2e-2, atol=3e-5 * float(ref.abs().max() + 1e-3)), n
+        assert _rel(p.grad.cpu(), sd_r[n].grad) < 0.25, n               # bf16 operands vs fp32 (as the ReLU network)
     for n, p in m.proposal_network.named_parameters():
-        ref = sd_p[n].grad
-        assert th.allclose(p.grad.cpu(), ref, rtol=5e-2, atol=5e-5 * float(ref.abs().max() + 1e-3)), n
+        assert _rel(p.grad.cpu(), sd_p[n].grad) < 0.35, n
 
 
 def test_garf_training_step_reduces_loss(cuda):
