@@ -119,6 +119,31 @@ int nerfb200_resample_icdf(const float* edges, const float* cdf, const float* u_
                            int Sc, int Sf, float* out_edges, int32_t* out_idx, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * a12 (rest of the chain). What GarfModel.forward obtains from nerfacc besides the importance
+ * sampling above (garf/model_garf.py:210-230,257; restated in oracle/ref_garf.py — parity unpinned):
+ *   lindisp_intervals: t = 1 / (s/far + (1-s)/near) for normalised edges s (B,E); any of t_edges (B,E),
+ *     t_start / t_end / delta / t_mid (B,E-1) may be NULL.
+ *   trans_cdf_fwd: trans (B,S) [or NULL] = exp(-exclusive cumsum(sigma * (t_end - t_start))),
+ *     cdf (B,S+1) = 1 - [trans, 0]  (render_transmittance_from_density at the proposal level).
+ *   trans_cdf_bwd: d_sigma (B,S) from g_cdf (B,S+1) and / or g_trans (B,S) (either may be NULL).
+ *   prop_loss: *loss += scale * sum clip(w - w_outer, 0)^2 / (w + eps) over the query bins
+ *     (PropNetEstimator.compute_loss, Mip-NeRF 360 eq. 13; w from cdf_query (B,Sq+1), the outer bound
+ *     from cdf_key (B,Sk+1) at the searchsorted bounds of t_query in t_key); d_cdf_key (B,Sk+1) or
+ *     NULL receives scale * d(sum)/d(cdf_key). The caller zeroes *loss; scale = 1 / (B * Sq) for the mean.
+ */
+int nerfb200_lindisp_intervals(const float* s_edges, float near, float far, int B, int E,
+                               float* t_edges, float* t_start, float* t_end, float* delta,
+                               float* t_mid, void* stream);
+int nerfb200_trans_cdf_fwd(const float* sigma, const float* t_start, const float* t_end, int B, int S,
+                           float* out_trans, float* out_cdf, void* stream);
+int nerfb200_trans_cdf_bwd(const float* sigma, const float* t_start, const float* t_end,
+                           const float* g_cdf, const float* g_trans, int B, int S, float* d_sigma,
+                           void* stream);
+int nerfb200_prop_loss(const float* t_query, const float* cdf_query, const float* t_key,
+                       const float* cdf_key, int B, int Sq, int Sk, float eps, float scale,
+                       float* loss, float* d_cdf_key, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * a13. Camera extrinsics (per-image so(3) rotation + translation).
  * Replaces CameraExtrinsics.forward / forward_origins / so3_to_SO3
  * (barf/model_camera_extrinsics.py:22-85): R_i = exp([w_i]x), o' = o + t_i, d' = R_i d.

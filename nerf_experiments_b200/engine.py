@@ -211,22 +211,40 @@ class TrainEngine:
             raise RuntimeError("capture: run one eager step() with a batch of this shape first")
         self.coarse_weight = coarse_weight
         self._static = [None if t is None else t.detach().clone() for t in batch]
-        self.flat.version += 1                    # the captured forward must contain the weight re-pack
         from ._lib import launch_count
+        import gc
+        self.last_logs = None
+        gc.collect()
         th.cuda.synchronize(self.device)
-        state_before = self.state.clone()
-        snap = [t.clone() for t in (self.flat.flat, self.exp_avg, self.exp_avg_sq)]
+        snap = [t.clone() for t in (self.flat.flat, self.exp_avg, self.exp_avg_sq, self.state)]
+
+        def restore():
+            for dst, src in zip((self.flat.flat, self.exp_avg, self.exp_avg_sq, self.state), snap):
+                dst.copy_(src)
+            self.flat.version += 1                # the next forward re-packs the weight images
+
+        # One eager run of the step ON THE CAPTURE STREAM first, then the capture on the same stream:
+        # whatever autograd keeps alive between steps (gradient accumulators of parameters a model holds
+        # a graph on, e.g. GarfModel's proposal cdf) then belongs to the capture stream. Accumulators
+        # left over from eager steps on the default stream make the autograd engine synchronise the
+        # capturing stream with it at the end of backward, which invalidates the capture
+        # (cudaErrorStreamCaptureIsolation, observed on B200 / torch 2.11).
+        cs = th.cuda.Stream(device=self.device)
+        cs.wait_stream(th.cuda.current_stream(self.device))
+        with th.cuda.stream(cs):
+            self._device_step(self._static)
+            restore()
+        cs.synchronize()
+        gc.collect()
         before = launch_count()
         self._graph = th.cuda.CUDAGraph()
-        with th.cuda.graph(self._graph, capture_error_mode="thread_local"):
+        with th.cuda.graph(self._graph, stream=cs, capture_error_mode="thread_local"):
             logs = self._device_step(self._static)
             self._static_logs = {k: v.detach() for k, v in logs.items()}
         self.launches_per_replay = launch_count() - before     # kernels of this library inside one replay
-        # capture does not execute, but keep the engine state exactly as it was in any case
-        self.state.copy_(state_before)
-        for dst, src in zip((self.flat.flat, self.exp_avg, self.exp_avg_sq), snap):
-            dst.copy_(src)
-        self.flat.version += 1
+        with th.cuda.stream(cs):
+            restore()                             # capture does not execute; keep the engine state exact anyway
+        th.cuda.current_stream(self.device).wait_stream(cs)
         return self
 
     def release_graph(self):

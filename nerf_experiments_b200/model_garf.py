@@ -29,9 +29,7 @@ class _CompositeNerfacc(th.autograd.Function):
     """nerfacc.rendering arithmetic on dense (B, S) samples: rgb, weights, opacity, depth."""
 
     @staticmethod
-    def forward(ctx, sigma, rgb, t_start, t_end):
-        delta = (t_end - t_start).contiguous()
-        t_mid = ((t_start + t_end) * 0.5).contiguous()
+    def forward(ctx, sigma, rgb, delta, t_mid):
         out_rgb, w, opacity, depth = ops.composite_fwd(sigma, delta, rgb, t_mid, _lib.COMPOSITE_NERFACC,
                                                        want_w=True, want_opacity=True, want_depth=True)
         ctx.save_for_backward(sigma.detach(), rgb.detach(), delta, t_mid)
@@ -50,22 +48,20 @@ class _CompositeNerfacc(th.autograd.Function):
 
 
 def transmittance_cdf(sigma: th.Tensor, t_start: th.Tensor, t_end: th.Tensor):
-    """trans = exp(-exclusive cumsum(sigma * delta)); cdf = 1 - [trans, 0]  (B, S+1)."""
-    sd = sigma * (t_end - t_start)
-    trans = th.exp(-(th.cumsum(sd, dim=1) - sd))
-    cdf = 1.0 - th.cat((trans, th.zeros_like(trans[:, :1])), dim=1)
-    return trans, cdf
+    """trans = exp(-exclusive cumsum(sigma * delta)); cdf = 1 - [trans, 0]  (B, S+1) — one kernel
+    (`ops.transmittance` without, `ops.transmittance_cdf` with gradient to sigma)."""
+    if th.is_grad_enabled() and sigma.requires_grad:
+        cdf = ops.transmittance_cdf(sigma, t_start, t_end)
+        return 1.0 - cdf[:, :-1], cdf
+    return ops.transmittance(sigma, t_start, t_end)
 
 
 def pdf_outer_loss(t_query: th.Tensor, cdf_query: th.Tensor, t_key: th.Tensor, cdf_key: th.Tensor,
                    eps: float = 1e-7) -> th.Tensor:
-    """nerfacc's proposal loss (Mip-NeRF 360 eq. 13): the key (proposal) histogram must bound the
-    query (radiance) histogram from above; only the excess is penalised."""
-    ids_right = th.searchsorted(t_key.contiguous(), t_query.contiguous(), right=False).clamp(0, t_key.shape[1] - 1)
-    ids_left = (th.searchsorted(t_key.contiguous(), t_query.contiguous(), right=True) - 1).clamp(0, t_key.shape[1] - 1)
-    w = cdf_query[:, 1:] - cdf_query[:, :-1]
-    w_outer = cdf_key.gather(1, ids_right[:, 1:]) - cdf_key.gather(1, ids_left[:, :-1])
-    return th.clip(w - w_outer, min=0) ** 2 / (w + eps)
+    """nerfacc's proposal loss (Mip-NeRF 360 eq. 13), mean over the query bins: the key (proposal)
+    histogram must bound the query (radiance) histogram from above; only the excess is penalised.
+    One kernel for the loss and its gradient w.r.t. the key cdf (`ops.proposal_loss`)."""
+    return ops.proposal_loss(t_query, cdf_query, t_key, cdf_key, eps)
 
 
 class GarfModel(LightningModule):
@@ -99,57 +95,69 @@ class GarfModel(LightningModule):
         self.radiance_network = RadianceNetwork(gaussian_init_min=gaussian_init_min,
                                                 gaussian_init_max=gaussian_init_max)
         self.automatic_optimization = False
-        self._prop_cache = None     # (t edges, cdf) of the proposal level of the last forward
 
     # -- sampling ----------------------------------------------------------------------------
     def _get_positions(self, ray_origs, ray_dirs, t_starts, t_ends):
+        """(B,S,3) sample positions. Kept for callers of the reference surface (garf/ray_logger.py:161-189);
+        the hot path never materialises them (the fused kernels form o + (t0 + t1) / 2 d in registers)."""
         return ray_origs[:, None] + ray_dirs[:, None] * ((t_starts + t_ends))[..., None] / 2
 
     def _s_to_t(self, s: th.Tensor) -> th.Tensor:
         """nerfacc "lindisp" spacing."""
         return 1.0 / (s / self.far_plane + (1.0 - s) / self.near_plane)
 
+    def _unit_edges(self, B: int, dev):
+        cache = getattr(self, "_edge_cache", None)
+        if cache is None or cache.shape[0] != B or cache.device != dev:
+            cache = th.tensor([0.0, 1.0], device=dev).repeat(B, 1).contiguous()
+            self._edge_cache = cache
+        return cache
+
     def _sampling(self, ray_origs, ray_dirs, u_rays):
-        """PropNetEstimator.sampling with one proposal level (garf/model_garf.py:210-220)."""
+        """PropNetEstimator.sampling with one proposal level (garf/model_garf.py:210-220): every stage is
+        one launch — inverse-CDF sampling, lindisp intervals, fused proposal network, transmittance ->
+        cdf. Returns the radiance intervals (t_start, t_end, delta, t_mid), their edges and the proposal
+        level's (edges, cdf) — handed on through `extras`, never kept on the module: a tensor with an
+        autograd graph that outlives its step would keep that step's gradient accumulators alive."""
         B = ray_origs.shape[0]
         dev = ray_origs.device
         stratified = self.training
         if stratified and u_rays is None:
             u_rays = (th.rand(B, device=dev), th.rand(B, device=dev))
         u_prop, u_rad = u_rays if stratified else (None, None)
-        s_edges = th.tensor([0.0, 1.0], device=dev).expand(B, 2).contiguous()
-        cdf = s_edges.clone()
+        s_edges = self._unit_edges(B, dev)
         # proposal level
-        s_edges = ops.resample_icdf(s_edges, cdf, self.proposal_samples_per_ray, u_prop)
-        t = self._s_to_t(s_edges)
-        t0, t1 = t[:, :-1].contiguous(), t[:, 1:].contiguous()
-        # the closure of garf/model_garf.py:127-141 (positions, network) as one fused launch on the rays
+        s_edges = ops.resample_icdf(s_edges, s_edges, self.proposal_samples_per_ray, u_prop)
+        t, t0, t1 = ops.lindisp_intervals(s_edges, self.near_plane, self.far_plane)
         sigma = self.proposal_network.forward_rays(ray_origs, ray_dirs, t0, t1)
         _, cdf = transmittance_cdf(sigma, t0, t1)
-        self._prop_cache = (t, cdf)
+        prop = (t, cdf)
         # radiance level
         s_edges = ops.resample_icdf(s_edges, cdf.detach(), self.radiance_samples_per_ray, u_rad)
-        t = self._s_to_t(s_edges)
-        return t[:, :-1].contiguous(), t[:, 1:].contiguous()
+        t, t0, t1, delta, t_mid = ops.lindisp_intervals(s_edges, self.near_plane, self.far_plane, want_mid=True)
+        return t0, t1, delta, t_mid, t, prop
 
     # -- forward -----------------------------------------------------------------------------
     def forward(self, ray_origs: th.Tensor, ray_dirs: th.Tensor, u_rays=None):
-        t_starts, t_ends = self._sampling(ray_origs, ray_dirs, u_rays)
+        t_starts, t_ends, delta, t_mid, t_edges, prop = self._sampling(ray_origs, ray_dirs, u_rays)
         rgb_s, sigma = self.radiance_network.forward_rays(ray_origs, ray_dirs, t_starts, t_ends)
-        rgb, weights, opacity, depth = _CompositeNerfacc.apply(sigma, rgb_s, t_starts, t_ends)
-        with th.no_grad():
-            trans, _ = transmittance_cdf(sigma, t_starts, t_ends)
+        rgb, weights, opacity, depth = _CompositeNerfacc.apply(sigma, rgb_s, delta, t_mid)
+        trans, cdf_q = ops.transmittance(sigma, t_starts, t_ends)
         extras = {"weights": weights, "trans": trans, "t_starts": t_starts, "t_ends": t_ends,
-                  "rgbs": rgb_s, "sigmas": sigma}
+                  "rgbs": rgb_s, "sigmas": sigma, "cdf": cdf_q, "t_edges": t_edges,
+                  "prop_t_edges": prop[0], "prop_cdf": prop[1]}
         return rgb, opacity[:, None], depth[:, None], extras
 
     def compute_proposal_loss(self, extras: Dict) -> th.Tensor:
         """PropNetEstimator.compute_loss(extras["trans"]) (garf/model_garf.py:257)."""
-        trans = extras["trans"].detach()
-        cdf_q = 1.0 - th.cat((trans, th.zeros_like(trans[:, :1])), dim=1)
-        t_q = th.cat((extras["t_starts"], extras["t_ends"][:, -1:]), dim=1)
-        t_k, cdf_k = self._prop_cache
-        return pdf_outer_loss(t_q, cdf_q, t_k, cdf_k).mean()
+        cdf_q = extras.get("cdf")
+        if cdf_q is None:
+            trans = extras["trans"].detach()
+            cdf_q = 1.0 - th.cat((trans, th.zeros_like(trans[:, :1])), dim=1)
+        t_q = extras.get("t_edges")
+        if t_q is None:
+            t_q = th.cat((extras["t_starts"], extras["t_ends"][:, -1:]), dim=1)
+        return pdf_outer_loss(t_q, cdf_q, extras["prop_t_edges"], extras["prop_cdf"])
 
     def _forward_loss(self, batch: InnerModelBatchInput, u_rays=None):
         ray_origs, ray_dirs, ray_colors = batch
@@ -157,6 +165,38 @@ class GarfModel(LightningModule):
         proposal_loss = self.compute_proposal_loss(extras)
         radiance_loss = nn.functional.mse_loss(ray_colors_pred, ray_colors)
         return ray_colors_pred, (proposal_loss, radiance_loss)
+
+    # -- engine surface (engine.TrainEngine): one flat buffer, fused Adam + ExponentialLR -----------------
+    def fused_networks(self):
+        return [self.proposal_network, self.radiance_network]
+
+    @property
+    def param_groups(self):
+        """The four groups of the reference's two Adam optimisers (garf/model_garf.py:365-428) as ONE
+        list for the fused optimiser: arithmetic per parameter is identical (same betas / eps)."""
+        if getattr(self, "_param_groups", None) is None:
+            groups = []
+            for net, lr0, lr1, n, wd in (
+                    (self.proposal_network, self.proposal_learning_rate_start, self.proposal_learning_rate_stop,
+                     self.proposal_learning_rate_decay_end, self.proposal_weight_decay),
+                    (self.radiance_network, self.radiance_learning_rate_start, self.radiance_learning_rate_stop,
+                     self.radiance_learning_rate_decay_end, self.radiance_weight_decay)):
+                gamma = self._calculate_decay_factor(lr0, lr1, n)
+                for params, factor in ((net.parameters_linear(), 1.0), (net.parameters_gaussian(), self.gaussian_learning_rate_factor)):
+                    groups.append({"parameters": list(params), "learning_rate_start": factor * lr0,
+                                   "learning_rate_stop": factor * lr1, "learning_rate_decay_end": n,
+                                   "weight_decay": wd, "schedule": "exponential", "gamma": gamma})
+            self._param_groups = groups
+        return self._param_groups
+
+    def training_loss(self, ray_origs, ray_dirs, ray_colors, u_prop=None, u_rad=None):
+        """Device part of training_step (no host synchronisation; capturable): the summed loss the
+        reference back-propagates (garf/model_garf.py:311) and the values it logs."""
+        u = (u_prop, u_rad) if u_prop is not None else None
+        _, (proposal_loss, radiance_loss) = self._forward_loss((ray_origs, ray_dirs, ray_colors), u)
+        logs = {"loss_fine": radiance_loss.detach(), "train_proposal_loss": proposal_loss.detach(),
+                "train_psnr": -10 * th.log10(radiance_loss.detach())}
+        return radiance_loss + proposal_loss, logs
 
     def _get_logging_losses(self, stage: Literal["train", "val", "test"], batch_idx: int,
                             proposal_loss: th.Tensor, radiance_loss: th.Tensor, *args, **kwargs):
@@ -217,3 +257,12 @@ class GarfModel(LightningModule):
             last_epoch=-self.radiance_learning_rate_decay_end - 1)
         return ([self._proposal_optimizer, self._radiance_optimizer],
                 [self._proposal_learning_rate_scheduler, self._radiance_learning_rate_scheduler])
+
+
+def garf_engine(model: GarfModel, device, process_group=None):
+    """engine.TrainEngine for a GarfModel: both networks in one flat parameter buffer, the whole step
+    (sampling, both fused networks, compositing, proposal loss, backward, all-reduce, fused Adam with the
+    four ExponentialLR groups) without host synchronisation. torch.optim.Adam's default eps (1e-8), as
+    the reference constructs its optimisers (garf/model_garf.py:367-409)."""
+    from .engine import TrainEngine
+    return TrainEngine(model, device, process_group=process_group, eps=1e-8, loss_fn=model.training_loss)

@@ -168,6 +168,102 @@ def resample_icdf(edges, cdf, n_out: int, u_ray: Optional[th.Tensor] = None, wan
     return (out, idx) if want_idx else out
 
 
+def lindisp_intervals(s_edges: th.Tensor, near: float, far: float, want_mid: bool = False):
+    """nerfacc's "lindisp" map t = 1 / (s / far + (1 - s) / near) of normalised edges (B, S+1) and the
+    intervals it defines: returns (t_edges (B,S+1), t_start (B,S), t_end (B,S)[, delta, t_mid]) from ONE
+    launch (garf/model_garf.py:210-220 through PropNetEstimator.sampling)."""
+    B, E = s_edges.shape
+    s_edges = _f32(s_edges.detach(), "s_edges", (B, E))
+    dev = s_edges.device
+    t = th.empty((B, E), device=dev)
+    t0, t1 = th.empty((B, E - 1), device=dev), th.empty((B, E - 1), device=dev)
+    delta = th.empty_like(t0) if want_mid else None
+    mid = th.empty_like(t0) if want_mid else None
+    with th.cuda.device(dev):
+        check(lib().nerfb200_lindisp_intervals(_ptr(s_edges), float(near), float(far), B, E, _ptr(t), _ptr(t0), _ptr(t1),
+                                               _ptr(delta), _ptr(mid), _stream()), "lindisp_intervals")
+    return (t, t0, t1, delta, mid) if want_mid else (t, t0, t1)
+
+
+class _TransCdf(th.autograd.Function):
+    """cdf (B, S+1) = 1 - [exp(-exclusive cumsum(sigma delta)), 0] — the proposal level of
+    PropNetEstimator.sampling (render_transmittance_from_density + the cdf of its weights); the gradient
+    reaches sigma only (the sample positions carry none in the reference)."""
+
+    @staticmethod
+    def forward(ctx, sigma, t_start, t_end):
+        B, S = sigma.shape
+        sigma = _f32(sigma, "sigma", (B, S))
+        t_start = _f32(t_start, "t_start", (B, S))
+        t_end = _f32(t_end, "t_end", (B, S))
+        cdf = th.empty((B, S + 1), device=sigma.device)
+        with th.cuda.device(sigma.device):
+            check(lib().nerfb200_trans_cdf_fwd(_ptr(sigma), _ptr(t_start), _ptr(t_end), B, S, None, _ptr(cdf),
+                                               _stream()), "trans_cdf_fwd")
+        ctx.save_for_backward(sigma.detach(), t_start, t_end)
+        return cdf
+
+    @staticmethod
+    def backward(ctx, g_cdf):
+        sigma, t_start, t_end = ctx.saved_tensors
+        B, S = sigma.shape
+        d_sigma = th.empty_like(sigma)
+        with th.cuda.device(sigma.device):
+            check(lib().nerfb200_trans_cdf_bwd(_ptr(sigma), _ptr(t_start), _ptr(t_end), _ptr(g_cdf.contiguous()), None,
+                                               B, S, _ptr(d_sigma), _stream()), "trans_cdf_bwd")
+        return d_sigma, None, None
+
+
+def transmittance_cdf(sigma: th.Tensor, t_start: th.Tensor, t_end: th.Tensor) -> th.Tensor:
+    return _TransCdf.apply(sigma, t_start, t_end)
+
+
+def transmittance(sigma: th.Tensor, t_start: th.Tensor, t_end: th.Tensor):
+    """(trans (B,S), cdf (B,S+1)) without gradient (the radiance level: extras["trans"])."""
+    B, S = sigma.shape
+    sigma = _f32(sigma.detach(), "sigma", (B, S))
+    trans = th.empty((B, S), device=sigma.device)
+    cdf = th.empty((B, S + 1), device=sigma.device)
+    with th.cuda.device(sigma.device):
+        check(lib().nerfb200_trans_cdf_fwd(_ptr(sigma), _ptr(_f32(t_start, "t_start", (B, S))),
+                                           _ptr(_f32(t_end, "t_end", (B, S))), B, S, _ptr(trans), _ptr(cdf), _stream()),
+              "trans_cdf_fwd")
+    return trans, cdf
+
+
+class _PropLoss(th.autograd.Function):
+    """mean( clip(w - w_outer, 0)^2 / (w + eps) ) — PropNetEstimator.compute_loss (garf/model_garf.py:257):
+    the key (proposal) histogram must bound the query (radiance) histogram from above. One launch
+    computes the loss and its gradient w.r.t. the key cdf (the only input that carries one)."""
+
+    @staticmethod
+    def forward(ctx, t_query, cdf_query, t_key, cdf_key, eps):
+        B, Eq = t_query.shape
+        Ek = t_key.shape[1]
+        t_query = _f32(t_query.detach(), "t_query", (B, Eq))
+        cdf_query = _f32(cdf_query.detach(), "cdf_query", (B, Eq))
+        t_key = _f32(t_key.detach(), "t_key", (B, Ek))
+        cdf_key_c = _f32(cdf_key.detach(), "cdf_key", (B, Ek))
+        loss = th.zeros((), device=t_query.device)
+        d_key = th.empty((B, Ek), device=t_query.device) if cdf_key.requires_grad else None
+        with th.cuda.device(t_query.device):
+            check(lib().nerfb200_prop_loss(_ptr(t_query), _ptr(cdf_query), _ptr(t_key), _ptr(cdf_key_c), B, Eq - 1, Ek - 1,
+                                           float(eps), 1.0 / float(B * (Eq - 1)), _ptr(loss), _ptr(d_key), _stream()),
+                  "prop_loss")
+        ctx.d_key = d_key
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        d = ctx.d_key
+        ctx.d_key = None
+        return None, None, None, (d * g if d is not None else None), None
+
+
+def proposal_loss(t_query, cdf_query, t_key, cdf_key, eps: float = 1e-7) -> th.Tensor:
+    return _PropLoss.apply(t_query, cdf_query, t_key, cdf_key, eps)
+
+
 # ---------------------------------------------------------------------------------------------
 # a13 camera extrinsics
 # ---------------------------------------------------------------------------------------------

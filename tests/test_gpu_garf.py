@@ -218,6 +218,87 @@ def test_garf_model_chain_matches_oracle(cuda, training):
         assert _rel(p.grad.cpu(), sd_p[n].grad) < 0.35, n
 
 
+@pytest.mark.parametrize("B,S", [(1, 1), (7, 33), (64, 64), (300, 192)])
+def test_propnet_chain_kernels_match_oracle(cuda, B, S):
+    """lindisp intervals, transmittance -> cdf (forward and backward) and the proposal loss with its
+    gradient, each one launch, against the oracle restatement and its autograd (oracle/ref_garf.py)."""
+    from nerf_experiments_b200 import ops
+    gen = th.Generator().manual_seed(B * 1000 + S)
+    s_edges = th.sort(th.rand((B, S + 1), generator=gen), dim=1).values
+    s_edges[:, 0], s_edges[:, -1] = 0.0, 1.0
+    t, t0, t1, delta, mid = ops.lindisp_intervals(s_edges.to(cuda), 2.0, 7.0, want_mid=True)
+    t_ref = 1.0 / (s_edges / 7.0 + (1.0 - s_edges) / 2.0)
+    assert th.allclose(t.cpu(), t_ref, rtol=2e-6) and th.equal(t0, t[:, :-1]) and th.equal(t1, t[:, 1:])
+    assert th.allclose(delta.cpu(), t_ref[:, 1:] - t_ref[:, :-1], rtol=1e-4, atol=1e-6)
+    assert th.allclose(mid.cpu(), (t_ref[:, 1:] + t_ref[:, :-1]) / 2, rtol=2e-6)
+
+    sigma = (th.nn.functional.softplus(th.randn((B, S), generator=gen)) * 2).requires_grad_()
+    r0, r1 = t_ref[:, :-1], t_ref[:, 1:]
+    trans_ref, cdf_ref = ref_garf.transmittance_cdf(sigma, r0, r1)
+    up = th.randn((B, S + 1), generator=gen)
+    (cdf_ref * up).sum().backward()
+    sc = sigma.detach().to(cuda).requires_grad_()
+    cdf = ops.transmittance_cdf(sc, r0.to(cuda), r1.to(cuda))
+    (cdf * up.to(cuda)).sum().backward()
+    assert th.allclose(cdf.detach().cpu(), cdf_ref.detach(), atol=2e-6)
+    assert th.allclose(sc.grad.cpu(), sigma.grad, rtol=1e-4, atol=1e-6)
+    tr, cdf2 = ops.transmittance(sc.detach(), r0.to(cuda), r1.to(cuda))
+    assert th.allclose(tr.cpu(), trans_ref.detach(), atol=2e-6) and th.equal(cdf2, cdf.detach())
+
+    # proposal loss: a coarser key histogram (every other edge, perturbed cdf) against the fine query one
+    Sk = max(S // 2, 1)
+    idx = th.linspace(0, S, Sk + 1).round().long()
+    t_k = t_ref[:, idx]
+    cdf_k = (cdf_ref.detach()[:, idx] * (0.7 + 0.6 * th.rand((B, Sk + 1), generator=gen))).clamp(0, 1)
+    cdf_k = th.sort(cdf_k, dim=1).values.requires_grad_()
+    loss_ref = ref_garf.pdf_outer_loss(t_ref, cdf_ref.detach(), t_k, cdf_k).mean()
+    loss_ref.backward()
+    ck = cdf_k.detach().to(cuda).requires_grad_()
+    loss = ops.proposal_loss(t_ref.to(cuda), cdf_ref.detach().to(cuda), t_k.to(cuda), ck)
+    (loss * 3.0).backward()
+    assert float(loss) == pytest.approx(float(loss_ref), rel=1e-4, abs=1e-9)
+    assert th.allclose(ck.grad.cpu() / 3.0, cdf_k.grad, rtol=1e-4, atol=1e-8)
+
+
+def test_garf_engine_matches_torch_optimisers(cuda):
+    """garf_engine (one flat buffer, fused Adam with the four ExponentialLR groups, captured graph) ==
+    the reference-shaped training_step with its two torch Adam optimisers and schedulers, step for step."""
+    from nerf_experiments_b200.model_garf import GarfModel, garf_engine
+    B = 192
+    gen = th.Generator().manual_seed(2)
+    batches = []
+    for _ in range(5):
+        o = th.nn.functional.normalize(th.randn((B, 3), generator=gen), dim=1) * 4.0
+        d = th.nn.functional.normalize(-o + 0.3 * th.randn((B, 3), generator=gen), dim=1)
+        batches.append(tuple(x.to(cuda) for x in (o, d, th.rand((B, 3), generator=gen), th.rand(B, generator=gen),
+                                                  th.rand(B, generator=gen))))
+    out = {}
+    for mode in ("torch", "engine", "graph"):
+        th.manual_seed(5)
+        m = GarfModel(2.0, 7.0, 16, 32, 0.5, 1.5, 2.0, 1e-3, 1e-4, 50, 0.0, 2e-3, 1e-4, 60, 0.0).to(cuda)
+        m.train()
+        losses = []
+        if mode == "torch":
+            for i, (o, d, c, u0, u1) in enumerate(batches):
+                losses.append(float(m.training_step((o, d, c), i, u_rays=(u0, u1))))
+            flat = th.cat([p.detach().reshape(-1) for g in m.param_groups for p in g["parameters"]])
+        else:
+            eng = garf_engine(m, cuda)
+            eng.step(*batches[0])
+            losses.append(float(eng.last_logs["loss_fine"] + eng.last_logs["train_proposal_loss"]))
+            if mode == "graph":
+                eng.capture(*batches[0])
+            for b in batches[1:]:
+                (eng.replay if mode == "graph" else eng.step)(*b)
+                losses.append(float(eng.last_logs["loss_fine"] + eng.last_logs["train_proposal_loss"]))
+            flat = eng.flat.flat.detach().clone()
+        out[mode] = (losses, flat)
+    for mode in ("engine", "graph"):
+        assert out[mode][0] == pytest.approx(out["torch"][0], rel=2e-3)
+        diff = (out[mode][1] - out["torch"][1]).abs()
+        assert float((diff > 5e-5).float().mean()) < 2e-3 and float(diff.max()) < 2e-2
+
+
 def test_garf_training_step_reduces_loss(cuda):
     from nerf_experiments_b200.model_garf import GarfModel
     th.manual_seed(5)
