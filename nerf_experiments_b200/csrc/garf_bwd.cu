@@ -108,14 +108,15 @@ garf_bwd_kernel(const __grid_constant__ GarfBwdParams p) {
         const int through = (int)g - 1 - st.wait_lag;
         const int kind = st.kind, nsl = st.n_slabs, flags = st.flags;
         // the forward's pre-activations of this layer: requested before the accumulator is waited for
-        uint4 zq[4][2];
+        // (two 64-column groups in flight; the next two are requested while these are consumed)
+        uint4 zq[2][2];
+        const uint8_t* zbase = ztile + (size_t)(st.z_stash < 0 ? 0 : st.z_stash) * NB_SLAB_BYTES;
         if (kind == NG_BSTEP_ACT) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < 2; ++j) {
             if (j < nsl) {
-              const uint8_t* zs = ztile + (size_t)(st.z_stash + j) * NB_SLAB_BYTES;
-              zq[j][0] = ldg128_stream(zs + off0);
-              zq[j][1] = ldg128_stream(zs + off1);
+              zq[j][0] = ldg128_stream(zbase + (size_t)j * NB_SLAB_BYTES + off0);
+              zq[j][1] = ldg128_stream(zbase + (size_t)j * NB_SLAB_BYTES + off1);
             }
           }
         }
@@ -146,53 +147,77 @@ garf_bwd_kernel(const __grid_constant__ GarfBwdParams p) {
           publish_step(sm, g, true, lane);
         } else if (kind == NG_BSTEP_ACT) {
           const int ncols = 64 * nsl;
-          const float* coef = sm.floats + st.coef_off + 16 * cq;
+          const float4* coef4 = reinterpret_cast<const float4*>(sm.floats + st.coef_off + 16 * cq);
           const bool direct = (flags & NG_F_DIRECT) != 0;
           const bool first = (flags & NG_F_FIRST_LAYER) != 0;
           const bool grads = want && (st.skip_src != 0);
+          const bool add_hold = (flags & NG_F_HOLD_ADD) != 0;
           const float* skip = sm.floats + ((grads && !first) ? st.skip_off : 0) + 16 * cq;
+          const uint32_t acc_q = tmem_lane + (uint32_t)(st.src_col + 16 * cq);
           float acc3[3] = {0.f, 0.f, 0.f};
+          uint32_t va[16], vb[16];
+          auto group = [&](const uint32_t (&v)[16], int j) {
+            uint32_t dp[8];
+            const uint32_t zz[8] = {zq[j & 1][0].x, zq[j & 1][0].y, zq[j & 1][0].z, zq[j & 1][0].w,
+                                    zq[j & 1][1].x, zq[j & 1][1].y, zq[j & 1][1].z, zq[j & 1][1].w};
+            if (j + 2 < nsl) {     // the slot is free again: request the group after the next
+              zq[j & 1][0] = ldg128_stream(zbase + (size_t)(j + 2) * NB_SLAB_BYTES + off0);
+              zq[j & 1][1] = ldg128_stream(zbase + (size_t)(j + 2) * NB_SLAB_BYTES + off1);
+            }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (j < nsl) {
-              uint32_t v[16], dp[8];
-              tmem_ld16(tmem_lane + (uint32_t)(st.src_col + 64 * j + 16 * cq), v);
-              tmem_ld_wait16(v);
-              const uint32_t zz[8] = {zq[j][0].x, zq[j][0].y, zq[j][0].z, zq[j][0].w,
-                                      zq[j][1].x, zq[j][1].y, zq[j][1].z, zq[j][1].w};
+            for (int q = 0; q < 4; ++q) {
+              const float4 c = coef4[16 * j + q];
+              const float cc[4] = {c.x, c.y, c.z, c.w};
+              float dz[4];
 #pragma unroll
-              for (int i = 0; i < 16; i += 2) {
-                float ga = __uint_as_float(v[i]), gb = __uint_as_float(v[i + 1]);
-                if ((flags & NG_F_HOLD_ADD) && j < 2) {
-                  ga += bf_lo(hold[j][i >> 1]);
-                  gb += bf_hi(hold[j][i >> 1]);
-                }
-                const float z0 = bf_lo(zz[i >> 1]), z1 = bf_hi(zz[i >> 1]);
-                const float t0 = z0 * coef[64 * j + i], t1 = z1 * coef[64 * j + i + 1];
-                const float dz0 = ga * ex2f(z0 * t0) * (t0 * kTwoLn2);     // g * y * (-2 v z)
-                const float dz1 = gb * ex2f(z1 * t1) * (t1 * kTwoLn2);
-                dp[i >> 1] = pack_bf16(dz0, dz1);
-                if (grads) {
-                  if (first) {
-                    const float* W = p.params + prog.w1_off + (long long)(st.gen_col0 + 64 * j + 16 * cq + i) * 3;
+              for (int e = 0; e < 4; ++e) {
+                const int i = 4 * q + e;
+                float ga = __uint_as_float(v[i]);
+                if (add_hold && j < 2) ga += (e & 1) ? bf_hi(hold[j][i >> 1]) : bf_lo(hold[j][i >> 1]);
+                const float z = (e & 1) ? bf_hi(zz[i >> 1]) : bf_lo(zz[i >> 1]);
+                const float t = z * cc[e];
+                dz[e] = ga * ex2f(z * t) * (t * kTwoLn2);                 // g * y * (-2 v z)
+              }
+              dp[2 * q] = pack_bf16(dz[0], dz[1]);
+              dp[2 * q + 1] = pack_bf16(dz[2], dz[3]);
+              if (grads) {
+                if (first) {
+                  const float* W = p.params + prog.w1_off + (long long)(st.gen_col0 + 64 * j + 16 * cq + 4 * q) * 3;
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) acc3[c] = fmaf(dz1, __ldg(W + 3 + c), fmaf(dz0, __ldg(W + c), acc3[c]));
-                  } else {
+                  for (int e = 0; e < 4; ++e)
 #pragma unroll
-                    for (int c = 0; c < 3; ++c)
-                      acc3[c] = fmaf(dz1, skip[c * ncols + 64 * j + i + 1], fmaf(dz0, skip[c * ncols + 64 * j + i], acc3[c]));
+                    for (int c3 = 0; c3 < 3; ++c3) acc3[c3] = fmaf(dz[e], __ldg(W + 3 * e + c3), acc3[c3]);
+                } else {
+#pragma unroll
+                  for (int c3 = 0; c3 < 3; ++c3) {
+                    const float4 k = *reinterpret_cast<const float4*>(skip + c3 * ncols + 64 * j + 4 * q);
+                    acc3[c3] = fmaf(dz[3], k.w, fmaf(dz[2], k.z, fmaf(dz[1], k.y, fmaf(dz[0], k.x, acc3[c3]))));
                   }
                 }
               }
-              if (direct) {
-                uint8_t* ds = dytile + (size_t)(st.y_stash + j) * NB_SLAB_BYTES;
-                stg128(ds + off0, dp[0], dp[1], dp[2], dp[3]);
-                stg128(ds + off1, dp[4], dp[5], dp[6], dp[7]);
-              } else {
-                const uint32_t sb = slab_base + (uint32_t)(st.out_slab + j) * NB_SLAB_BYTES;
-                sts128g(sb + off0, dp[0], dp[1], dp[2], dp[3]);
-                sts128g(sb + off1, dp[4], dp[5], dp[6], dp[7]);
-              }
+            }
+            if (direct) {
+              uint8_t* ds = dytile + (size_t)(st.y_stash + j) * NB_SLAB_BYTES;
+              stg128(ds + off0, dp[0], dp[1], dp[2], dp[3]);
+              stg128(ds + off1, dp[4], dp[5], dp[6], dp[7]);
+            } else {
+              const uint32_t sb = slab_base + (uint32_t)(st.out_slab + j) * NB_SLAB_BYTES;
+              sts128g(sb + off0, dp[0], dp[1], dp[2], dp[3]);
+              sts128g(sb + off1, dp[4], dp[5], dp[6], dp[7]);
+            }
+          };
+          tmem_ld16(acc_q, va);
+#pragma unroll
+          for (int j = 0; j < 4; j += 2) {
+            if (j < nsl) {
+              tmem_ld_wait16(va);
+              if (j + 1 < nsl) tmem_ld16(acc_q + (uint32_t)(64 * (j + 1)), vb);
+              group(va, j);
+            }
+            if (j + 1 < nsl) {
+              tmem_ld_wait16(vb);
+              if (j + 2 < nsl) tmem_ld16(acc_q + (uint32_t)(64 * (j + 2)), va);
+              group(vb, j + 1);
             }
           }
           if (grads) {

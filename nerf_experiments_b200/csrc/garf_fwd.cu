@@ -132,7 +132,11 @@ garf_fwd_kernel(const __grid_constant__ GarfFwdParams p) {
             zp[r] = pack_bf16(z0, z1);
           }
           publish_step(sm, g, true, lane);
+#ifndef NG_EXP_NO_Z
           if (training && st.z_stash >= 0) {
+#else
+          if (false) {
+#endif
             uint8_t* zs = ztile + (size_t)(st.z_stash + sib) * NB_SLAB_BYTES;
 #pragma unroll
             for (int r = 0; r < 16; ++r)
@@ -140,38 +144,64 @@ garf_fwd_kernel(const __grid_constant__ GarfFwdParams p) {
           }
         } else if (kind == NG_STEP_ACT) {
           const int ncols = 64 * nsl;
-          const float* bias = sm.floats + st.bias_off + 16 * cq;
-          const float* coef = sm.floats + st.coef_off + 16 * cq;
+          const float4* bias4 = reinterpret_cast<const float4*>(sm.floats + st.bias_off + 16 * cq);
+          const float4* coef4 = reinterpret_cast<const float4*>(sm.floats + st.coef_off + 16 * cq);
           const bool has_skip = st.skip_src != 0;
           const float* skip = sm.floats + (has_skip ? st.skip_off : 0) + 16 * cq;
           const float sx = st.skip_src == 2 ? md.x : mp.x, sy = st.skip_src == 2 ? md.y : mp.y,
                       sz = st.skip_src == 2 ? md.z : mp.z;
+          const uint32_t acc_q = tmem_lane + (uint32_t)(st.src_col + 16 * cq);
           uint32_t zp[4][8];
+          uint32_t va[16], vb[16];
+          // one 16-column group: bias (+ rank-3 fp32 skip), Gaussian, bf16 packs of y (-> slab) and z (-> stash)
+          auto group = [&](const uint32_t (&v)[16], int j) {
+            uint32_t yp[8];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (j < nsl) {
-              uint32_t v[16], yp[8];
-              tmem_ld16(tmem_lane + (uint32_t)(st.src_col + 64 * j + 16 * cq), v);
-              tmem_ld_wait16(v);
-#pragma unroll
-              for (int i = 0; i < 16; i += 2) {
-                float z0 = __uint_as_float(v[i]) + bias[64 * j + i];
-                float z1 = __uint_as_float(v[i + 1]) + bias[64 * j + i + 1];
-                if (has_skip) {
-                  z0 = fmaf(skip[2 * ncols + 64 * j + i], sz, fmaf(skip[ncols + 64 * j + i], sy, fmaf(skip[64 * j + i], sx, z0)));
-                  z1 = fmaf(skip[2 * ncols + 64 * j + i + 1], sz, fmaf(skip[ncols + 64 * j + i + 1], sy, fmaf(skip[64 * j + i + 1], sx, z1)));
-                }
-                const float y0 = ex2f(z0 * z0 * coef[64 * j + i]), y1 = ex2f(z1 * z1 * coef[64 * j + i + 1]);
-                yp[i >> 1] = pack_bf16(y0, y1);
-                zp[j][i >> 1] = pack_bf16(z0, z1);
+            for (int q = 0; q < 4; ++q) {
+              const float4 b = bias4[16 * j + q], c = coef4[16 * j + q];
+              float z0 = __uint_as_float(v[4 * q]) + b.x, z1 = __uint_as_float(v[4 * q + 1]) + b.y;
+              float z2 = __uint_as_float(v[4 * q + 2]) + b.z, z3 = __uint_as_float(v[4 * q + 3]) + b.w;
+              if (has_skip) {
+                const float4 kx = *reinterpret_cast<const float4*>(skip + 64 * j + 4 * q);
+                const float4 ky = *reinterpret_cast<const float4*>(skip + ncols + 64 * j + 4 * q);
+                const float4 kz = *reinterpret_cast<const float4*>(skip + 2 * ncols + 64 * j + 4 * q);
+                z0 = fmaf(kz.x, sz, fmaf(ky.x, sy, fmaf(kx.x, sx, z0)));
+                z1 = fmaf(kz.y, sz, fmaf(ky.y, sy, fmaf(kx.y, sx, z1)));
+                z2 = fmaf(kz.z, sz, fmaf(ky.z, sy, fmaf(kx.z, sx, z2)));
+                z3 = fmaf(kz.w, sz, fmaf(ky.w, sy, fmaf(kx.w, sx, z3)));
               }
-              const uint32_t sb = slab_base + (uint32_t)(st.out_slab + j) * NB_SLAB_BYTES;
-              sts128g(sb + off0, yp[0], yp[1], yp[2], yp[3]);
-              sts128g(sb + off1, yp[4], yp[5], yp[6], yp[7]);
+              const float y0 = ex2f(z0 * z0 * c.x), y1 = ex2f(z1 * z1 * c.y);
+              const float y2 = ex2f(z2 * z2 * c.z), y3 = ex2f(z3 * z3 * c.w);
+              yp[2 * q] = pack_bf16(y0, y1);
+              yp[2 * q + 1] = pack_bf16(y2, y3);
+              zp[j][2 * q] = pack_bf16(z0, z1);
+              zp[j][2 * q + 1] = pack_bf16(z2, z3);
+            }
+            const uint32_t sb = slab_base + (uint32_t)(st.out_slab + j) * NB_SLAB_BYTES;
+            sts128g(sb + off0, yp[0], yp[1], yp[2], yp[3]);
+            sts128g(sb + off1, yp[4], yp[5], yp[6], yp[7]);
+          };
+          // the TMEM load of group j + 1 is in flight during the math of group j
+          tmem_ld16(acc_q, va);
+#pragma unroll
+          for (int j = 0; j < 4; j += 2) {
+            if (j < nsl) {
+              tmem_ld_wait16(va);
+              if (j + 1 < nsl) tmem_ld16(acc_q + (uint32_t)(64 * (j + 1)), vb);
+              group(va, j);
+            }
+            if (j + 1 < nsl) {
+              tmem_ld_wait16(vb);
+              if (j + 2 < nsl) tmem_ld16(acc_q + (uint32_t)(64 * (j + 2)), va);
+              group(vb, j + 1);
             }
           }
           publish_step(sm, g, true, lane);
+#ifndef NG_EXP_NO_Z
           if (training && st.z_stash >= 0) {
+#else
+          if (false) {
+#endif
             // after the publication: a global store in flight would make the proxy fence wait for its ack
 #pragma unroll
             for (int j = 0; j < 4; ++j) {

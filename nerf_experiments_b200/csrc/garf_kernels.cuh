@@ -200,8 +200,10 @@ __device__ __forceinline__ void stash_copier_loop(const NgProgram& prog, const G
       if (st.y_stash >= 0 && st.out_slab >= 0 && !(st.flags & NG_F_DIRECT)) {
         const int extra = (st.kind == NG_BSTEP_PLAIN && (st.flags & NG_F_SIGMA)) ? 1 : 0;
         const int n = st.n_slabs + extra;
+#ifndef NG_EXP_NO_Y
         for (int j = 0; j < n; ++j)
           bulk_s2g(tile_stash + (size_t)(st.y_stash + j) * NB_SLAB_BYTES, sm.slab(st.out_slab + j), NB_SLAB_BYTES);
+#endif
         bulk_commit();
         bulk_wait_read<0>();
       }
