@@ -237,6 +237,27 @@ int nerfb200_mlp_workspace_bytes(const void* program_host, long long n_samples,
                                  long long* stash_bytes, long long* mask_bytes);
 
 /* ------------------------------------------------------------------------------------------
+ * The inner fused op of BASELINE.json's north_star — forward(rays_o, rays_d, near, far) -> rgb, depth,
+ * weights — as one call: uniform t-sampling (barf/model_interpolation.py:135-180), fused field (:288-312,
+ * barf/model_interpolation_architecture.py:96-141) and compositing (:316-353) enqueued back to back.
+ * Inference only (no activation stash). rays_o, rays_d (B,3); pixel_width (B) or NULL; t_start / t_end
+ * (B,S): the sample bins, or both NULL for uniform sampling with jitter (B,S) / offset_u (B) or NULL as
+ * in nerfb200_sample_uniform; t_mode 0 = "left", 1 = "middle"; flavour NERFB200_COMPOSITE_*.
+ * out_rgb (B,3); out_depth (B) = sum w t_mid / max(sum w, eps), out_weights (B,S), out_opacity (B)
+ * = sum w: each of the three may be NULL. workspace:
+ * nerfb200_render_rays_workspace_bytes(B, S) bytes, caller-owned.
+ */
+int nerfb200_render_rays_workspace_bytes(int B, int S, long long* bytes);
+int nerfb200_render_rays(const void* program_host, const void* wpack, const float* bias,
+                         int n_bias_floats, const NbPeCfg* pe_pos_host, const NbPeCfg* pe_dir_host,
+                         const float* alpha_pos, const float* alpha_dir, float sigma_bias,
+                         const float* rays_o, const float* rays_d, const float* pixel_width, int B, int S,
+                         float near_t, float far_t, const float* t_start, const float* t_end,
+                         const float* jitter, const float* offset_u,
+                         float offset_size, int t_mode, int flavour, void* workspace, float* out_rgb,
+                         float* out_depth, float* out_weights, float* out_opacity, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * a7, a8 (+ a6 inside). Fused GARF field: RadianceNetwork.forward (garf/model_radiance.py:84-96,
  * == barf/model_garf_radiance.py:101-113) and ProposalNetwork.forward (garf/model_proposal.py:55-56)
  * with the Gaussian activation (barf/gaussian.py:10-31) and their autograd, on per-ray or

@@ -210,6 +210,9 @@ def _declare(L):
     L.nerfb200_pe_bwd.argtypes = [C.POINTER(NbPeCfg), vp, vp, vp, vp, vp, vp, vp, C.c_longlong, vp, vp, vp]
     L.nerfb200_act_fwd.argtypes = [i32, vp, vp, vp, C.c_longlong, i32, vp, i32, vp]
     L.nerfb200_act_bwd.argtypes = [i32, vp, vp, vp, vp, C.c_longlong, i32, vp, vp, vp, vp, i32, vp]
+    L.nerfb200_render_rays_workspace_bytes.argtypes = [i32, i32, C.POINTER(C.c_longlong)]
+    L.nerfb200_render_rays.argtypes = [vp, vp, vp, i32, C.POINTER(NbPeCfg), C.POINTER(NbPeCfg), vp, vp, f32, vp, vp, vp,
+                                       i32, i32, f32, f32, vp, vp, vp, vp, f32, i32, i32, vp, vp, vp, vp, vp, vp]
     L.nerfb200_lindisp_intervals.argtypes = [vp, f32, f32, i32, i32, vp, vp, vp, vp, vp, vp]
     L.nerfb200_trans_cdf_fwd.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp]
     L.nerfb200_trans_cdf_bwd.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp, vp]
@@ -231,7 +234,7 @@ EXPORTS = [
     "nerfb200_pose_fwd", "nerfb200_pose_bwd", "nerfb200_so3_to_SO3",
     "nerfb200_mlp_pack", "nerfb200_mlp_fwd", "nerfb200_mlp_fwd2", "nerfb200_mlp_bwd", "nerfb200_mlp_wgrad", "nerfb200_pe_fwd", "nerfb200_pe_bwd",
     "nerfb200_mlp_workspace_bytes", "nerfb200_garf_workspace_bytes", "nerfb200_garf_fwd", "nerfb200_garf_bwd",
-    "nerfb200_lindisp_intervals", "nerfb200_trans_cdf_fwd", "nerfb200_trans_cdf_bwd", "nerfb200_prop_loss",
+    "nerfb200_render_rays_workspace_bytes", "nerfb200_render_rays", "nerfb200_lindisp_intervals", "nerfb200_trans_cdf_fwd", "nerfb200_trans_cdf_bwd", "nerfb200_prop_loss",
     "nerfb200_adam_step", "nerfb200_adam_step_dev", "nerfb200_act_fwd", "nerfb200_act_bwd", "nerfb200_ray_batch", "nerfb200_kabsch",
 ]
 

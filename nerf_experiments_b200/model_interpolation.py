@@ -158,6 +158,66 @@ class NerfInterpolation(LightningModule):
             rgb_coarse = None
         return rgb_fine, rgb_coarse
 
+    # ---- the inner fused op: forward(rays_o, rays_d, near, far) -> rgb, depth, weights ------------
+    @th.no_grad()
+    def render(self, ray_origs: th.Tensor, ray_dirs: th.Tensor, pixel_width: th.Tensor = None,
+               near: float = None, far: float = None):
+        """(rgb (B,3), depth (B,), weights (B,S)) of the radiance pass — BASELINE.json's north-star
+        signature (near / far default to the module's planes). Each pass is ONE call of the C ABI
+        (`nerfb200_render_rays`: sampling -> fused field -> compositing); with a proposal network the
+        coarse pass's weights feed the pdf resampler and the fine pass renders on its bins.
+        depth = sum w t_mid / max(sum w, eps) (what GarfModel returns through nerfacc, garf/model_garf.py:
+        223-236; the barf module itself never computes one)."""
+        import ctypes as C
+        from ._lib import COMPOSITE_BARF, check, lib
+        from .field_function import _prep
+        near = self.near_sphere_normalized if near is None else near
+        far = self.far_sphere_normalized if far is None else far
+        o = ops._f32(ray_origs, "ray_origs")
+        d = ops._f32(ray_dirs, "ray_dirs", tuple(o.shape))
+        B, dev = o.shape[0], o.device
+        pw = None if pixel_width is None else _prep(pixel_width, B, 1, dev)
+        t_mode = {"left": 0, "middle": 1}[self.integration_strategy]
+        if self.uniform_sampling_strategy not in ("stratified_uniform", "equidistant"):
+            raise ValueError(f"sampling_strategy must be one of {uniform_sampling_strategies.__args__}")
+
+        def one_pass(model, S, t0=None, t1=None):
+            field = model.fused_field()
+            cm = field.prepare(dev)
+            cp, cd = field.pe_cfgs()
+            jitter = offset_u = None
+            if t0 is None:
+                if self.uniform_sampling_strategy == "stratified_uniform":
+                    jitter = th.rand((B, S), device=dev)
+                if self.uniform_sampling_offset_size != 0:
+                    offset_u = th.rand((B, 1), device=dev).reshape(-1)
+            nbytes = C.c_longlong()
+            check(lib().nerfb200_render_rays_workspace_bytes(B, S, C.byref(nbytes)), "render_rays_workspace_bytes")
+            ws = th.empty(max(nbytes.value, 4), device=dev, dtype=th.uint8)
+            rgb, depth = th.empty((B, 3), device=dev), th.empty((B,), device=dev)
+            w = th.empty((B, S), device=dev)
+            with th.cuda.device(dev):
+                check(lib().nerfb200_render_rays(
+                    C.byref(cm.program), field.wpack.data_ptr(), field.bias.data_ptr(), cm.bias_floats, C.byref(cp),
+                    C.byref(cd), ops._ptr(field.pe_pos.alpha_tensor()), ops._ptr(field.pe_dir.alpha_tensor()),
+                    float(field.sigma_bias), o.data_ptr(), d.data_ptr(), ops._ptr(pw), B, S, float(near), float(far),
+                    ops._ptr(t0), ops._ptr(t1), ops._ptr(jitter), ops._ptr(offset_u),
+                    float(self.uniform_sampling_offset_size), t_mode, COMPOSITE_BARF, ws.data_ptr(), rgb.data_ptr(),
+                    depth.data_ptr(), w.data_ptr(), None, th.cuda.current_stream().cuda_stream), "render_rays")
+            return rgb, depth, w, ws
+
+        if not self.proposal:
+            rgb, depth, w, _ = one_pass(self.model_radiance, self.samples_per_ray_radiance)
+            return rgb, depth, w
+        Sc = self.samples_per_ray_proposal
+        _, _, w_c, ws = one_pass(self.model_proposal, Sc)
+        n = B * Sc
+        ws_f = ws.view(th.float32)
+        t_c0, dist_c = ws_f[:n].view(B, Sc), ws_f[2 * n: 3 * n].view(B, Sc)
+        t_f0, t_f1 = self._sample_t_pdf_weighted(t_c0, w_c, dist_c, self.samples_per_ray_radiance)
+        rgb, depth, w, _ = one_pass(self.model_radiance, self.samples_per_ray_radiance, t_f0, t_f1)
+        return rgb, depth, w
+
     # ---- Lightning surface -------------------------------------------------------------------
     def _step_helper(self, batch, batch_idx, purpose: Literal["train", "val"]):
         (ray_origs_raw, ray_origs_pred, ray_dirs_raw, ray_dirs_pred, ray_colors_raw, img_idx, pixel_width) = batch

@@ -16,7 +16,7 @@ unmodified reference modules from ``/root/reference`` (with the stub packages un
 ``tests/golden/``; ``tests/test_oracle_golden.py`` checks every oracle function against those
 fixtures, and the closed-form known-answer checks of the reference's notebook
 (``barf/bug_hunting_with_Lauge.ipynb`` cells 8, 30, 40-42) are re-encoded in
-``tests/test_oracle_kat.py``.
+``tests/test_oracle_golden.py`` (meshgrid / orthogonality / value-range checks) and ``tests/test_host_logic.py``.
 
 Exception — parity unpinned: ``ref_nerfacc`` restates nerfacc's importance sampling, whose
 source is not part of the reference tree and which is not installed here (see that module).
