@@ -120,6 +120,18 @@ garf_bwd_kernel(const __grid_constant__ GarfBwdParams p) {
             }
           }
         }
+        // ... and the lines of the NEXT Gaussian step are pulled into L2 now (one 128-byte row segment per
+        // slab and row, by the quarter-0 thread): its loads then cost an L2 hit instead of an HBM round trip
+        if (cq == 0) {
+          for (int kn = k + 1; kn <= n_ops; ++kn) {
+            const NgStep& sn = prog.steps[kn];
+            if (sn.kind != NG_BSTEP_ACT) continue;
+            const uint8_t* zn = ztile + (size_t)sn.z_stash * NB_SLAB_BYTES + (uint32_t)row * 128u;
+            for (int j = 0; j < sn.n_slabs; ++j)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(zn + (size_t)j * NB_SLAB_BYTES));
+            break;
+          }
+        }
         rs.acc_through(sm, through);
         rs.drain_through(sm, through);
         tcgen05_fence_after();

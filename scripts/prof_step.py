@@ -1,22 +1,36 @@
-"""Small driver for ncu: a few BARF training steps of the bench workload (no timing)."""
+"""Small driver for ncu: a few training steps (no timing).
+usage: prof_step.py barf [rays] [steps]   BarfModel.training_step semantics of the bench workload (eager)
+       prof_step.py garf [rays] [steps]   GARF step (garf/main.py shape: 64 + 192 samples)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch as th
 import bench
-from nerf_experiments_b200.engine import TrainEngine
 
-rays = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+which = sys.argv[1] if len(sys.argv) > 1 else "barf"
+rays = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+steps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 dev = th.device("cuda:0")
-model = bench.build_model(20)
-eng = TrainEngine(model, dev)
-g = th.Generator().manual_seed(0)
-o = (th.nn.functional.normalize(th.randn((rays, 3), generator=g), dim=1) * 4.0).to(dev)
-d = th.nn.functional.normalize(-o.cpu() + 0.3 * th.randn((rays, 3), generator=g), dim=1).to(dev)
-target = th.rand((rays, 3), generator=g).to(dev)
-idx = th.randint(0, 20, (rays,), generator=g).int().to(dev)
-pw = th.full((rays, 1), 1 / 555.0, device=dev)
-for s in range(steps):
-    loss = eng.step(o, d, target, idx, pw)
+if which == "barf":
+    from nerf_experiments_b200 import scene
+    from nerf_experiments_b200.engine import TrainEngine
+    sc = scene.make_scene(bench.N_IMAGES, 200, 200, dev, rotation_noise=0.15, translation_noise=0.15, blur_sigmas=bench.BLUR_SIGMAS)
+    model = bench.build_barf_model(sc, len(sc.batcher) // rays)
+    eng = TrainEngine(model, dev, loss_fn=model.training_loss)
+    g = th.Generator(device=dev).manual_seed(0)
+    idx = th.randint(0, len(sc.batcher), (steps, rays), device=dev, generator=g)
+    for s in range(steps):
+        loss = eng.step(*sc.batcher.batch(idx[s]))
+else:
+    from nerf_experiments_b200.model_garf import GarfModel, garf_engine
+    th.manual_seed(1337)
+    m = GarfModel(2.0, 7.0, 64, 192, 0.5, 1.5, 1.0, 1e-3, 1e-4, 100000, 0.0, 1e-3, 1e-4, 100000, 0.0).to(dev)
+    m.train()
+    eng = garf_engine(m, dev)
+    g = th.Generator().manual_seed(0)
+    o = (th.nn.functional.normalize(th.randn((rays, 3), generator=g), dim=1) * 4.0).to(dev)
+    d = th.nn.functional.normalize(-o.cpu() + 0.3 * th.randn((rays, 3), generator=g), dim=1).to(dev)
+    tgt = th.rand((rays, 3), generator=g).to(dev)
+    for s in range(steps):
+        loss = eng.step(o, d, tgt)
 th.cuda.synchronize()
-print("loss", loss.item())
+print("loss", float(loss))
