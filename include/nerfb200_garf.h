@@ -39,7 +39,8 @@ enum {
   NG_N_SLABS = 6,           /* shared-memory slabs: 0..3 work, 4..5 hold / small blocks        */
   NG_N_STAGES = 3,          /* weight ring stages of 32 KB                                     */
   NG_GEN_COLS = 128,        /* columns of the first layer one NG_STEP_GEN produces (2 slabs)   */
-  NG_MAX_FLOATS = 7680      /* packed fp32 values staged in shared memory                      */
+  NG_MAX_FLOATS = 7680      /* fp32 slots of the shared-memory region holding the packed values; a */
+                            /* program may use 6900 (the kernels keep its step / op tables behind) */
 };
 
 /* step kinds (forward) */
@@ -62,8 +63,8 @@ enum {
   NG_F_HOLD_SAVE = 2,
   NG_F_HOLD_ADD = 4,
   NG_F_DIRECT = 8,          /* backward: dz goes straight to the HBM stash, no shared-memory slab */
-  NG_F_FIRST_LAYER = 16     /* backward: z / y of the network's first layer (z recomputed in fp32 */
-                            /* from xyz is NOT used: the forward stash holds z for every layer)   */
+  NG_F_FIRST_LAYER = 16     /* backward: this step differentiates the network's first layer: the  */
+                            /* input gradient uses its fp32 weights (w1_off, gen_col0) directly   */
 };
 
 typedef struct {

@@ -110,6 +110,7 @@ WGRAD_MMA, WGRAD_COLSUM = 0, 1
 
 # ---- mirrors of include/nerfb200_garf.h ------------------------------------------------------
 NG_MAX_OPS, NG_MAX_CHUNKS, NG_N_SLABS, NG_GEN_COLS, NG_MAX_FLOATS = 32, 6, 6, 128, 7680
+NG_MAX_PROGRAM_FLOATS = 6900   # NG_MAX_FLOATS minus the step / op tables the kernels keep in the same region
 NG_STEP_NONE, NG_STEP_GEN, NG_STEP_ACT, NG_STEP_LINEAR, NG_STEP_RGB, NG_STEP_SIGMA = range(6)
 NG_BSTEP_HEAD, NG_BSTEP_ACT, NG_BSTEP_PLAIN = 8, 9, 10
 NG_F_SIGMA, NG_F_HOLD_SAVE, NG_F_HOLD_ADD, NG_F_DIRECT, NG_F_FIRST_LAYER = 1, 2, 4, 8, 16

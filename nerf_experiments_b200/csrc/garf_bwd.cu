@@ -51,6 +51,7 @@ garf_bwd_kernel(const __grid_constant__ GarfBwdParams p) {
 
   if (threadIdx.x == 0) sm.init_barriers();
   for (int i = threadIdx.x; i < prog.n_floats; i += blockDim.x) sm.floats[i] = p.floats[i];
+  sm.load_tables(prog);
   if (warp == kMmaWarpG) tmem_alloc(sm.tmem_ptr, kTmemColsG);
   tcgen05_fence_before();
   __syncthreads();
@@ -103,7 +104,7 @@ garf_bwd_kernel(const __grid_constant__ GarfBwdParams p) {
         for (int i = 0; i < 8; ++i) hold[j][i] = 0u;
 
       for (int k = 0; k <= n_ops; ++k) {
-        const NgStep& st = prog.steps[k];
+        const NgStep& st = sm.steps[k];
         const uint32_t g = g0 + (uint32_t)k;
         const int through = (int)g - 1 - st.wait_lag;
         const int kind = st.kind, nsl = st.n_slabs, flags = st.flags;
@@ -124,7 +125,7 @@ garf_bwd_kernel(const __grid_constant__ GarfBwdParams p) {
         // slab and row, by the quarter-0 thread): its loads then cost an L2 hit instead of an HBM round trip
         if (cq == 0) {
           for (int kn = k + 1; kn <= n_ops; ++kn) {
-            const NgStep& sn = prog.steps[kn];
+            const NgStep& sn = sm.steps[kn];
             if (sn.kind != NG_BSTEP_ACT) continue;
             const uint8_t* zn = ztile + (size_t)sn.z_stash * NB_SLAB_BYTES + (uint32_t)row * 128u;
             for (int j = 0; j < sn.n_slabs; ++j)

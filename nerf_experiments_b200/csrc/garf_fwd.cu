@@ -43,6 +43,7 @@ garf_fwd_kernel(const __grid_constant__ GarfFwdParams p) {
 
   if (threadIdx.x == 0) sm.init_barriers();
   for (int i = threadIdx.x; i < prog.n_floats; i += blockDim.x) sm.floats[i] = p.floats[i];
+  sm.load_tables(prog);
   if (warp == kMmaWarpG) tmem_alloc(sm.tmem_ptr, kTmemColsG);
   tcgen05_fence_before();
   __syncthreads();
@@ -100,7 +101,7 @@ garf_fwd_kernel(const __grid_constant__ GarfFwdParams p) {
       }
 
       for (int k = 0; k <= n_ops; ++k) {
-        const NgStep& st = prog.steps[k];
+        const NgStep& st = sm.steps[k];
         const uint32_t g = g0 + (uint32_t)k;
         const int through = (int)g - 1 - st.wait_lag;
         const int kind = st.kind, nsl = st.n_slabs;

@@ -36,6 +36,9 @@ constexpr uint32_t kTmemColsG = 512;
 struct GarfSmem {
   static constexpr uint32_t kCtrlBytes = 512;
   static constexpr uint32_t kXyzBytes = 2u * NB_TILE_ROWS * 16u;   // float4 position + float4 direction per row
+  static constexpr uint32_t kStepTableBytes = (uint32_t)((sizeof(NgStep) * (NG_MAX_OPS + 1) + 15) / 16 * 16);
+  static constexpr uint32_t kTableBytes = kStepTableBytes + (uint32_t)((sizeof(NgOp) * NG_MAX_OPS + 15) / 16 * 16);
+  static constexpr uint32_t kMaxProgramFloats = (uint32_t)NG_MAX_FLOATS - kTableBytes / 4u;   // what a program may pack
   __host__ __device__ static constexpr uint32_t bytes() {
     return (uint32_t)NG_N_SLABS * NB_SLAB_BYTES + (uint32_t)NG_N_STAGES * NB_RING_STAGE_BYTES + kCtrlBytes +
            kXyzBytes + (uint32_t)NG_MAX_FLOATS * 4u;
@@ -50,7 +53,10 @@ struct GarfSmem {
   uint32_t* tmem_ptr;
   float4* pos;          // [128] query position of every tile row
   float4* dir;          // [128] ray direction of every tile row
-  float* floats;        // [NG_MAX_FLOATS]
+  float* floats;        // [NG_MAX_FLOATS]: packed fp32 values, and behind them (at the end of the region)
+  NgStep* steps;        // [NG_MAX_OPS + 1] the program's step and op tables: kernel parameters live in the
+  NgOp* ops;            // [NG_MAX_OPS]     constant bank, where a dynamically indexed field costs a dependent
+                        //                  ~100-cycle LDC each (10 % of the stall samples of the first version)
 
   __device__ explicit GarfSmem(uint8_t* b) : base(b) {
     ring_base = b + (uint32_t)NG_N_SLABS * NB_SLAB_BYTES;
@@ -64,6 +70,18 @@ struct GarfSmem {
     pos = reinterpret_cast<float4*>(c + kCtrlBytes);
     dir = pos + NB_TILE_ROWS;
     floats = reinterpret_cast<float*>(c + kCtrlBytes + kXyzBytes);
+    uint8_t* tables = c + kCtrlBytes + kXyzBytes + (uint32_t)NG_MAX_FLOATS * 4u - kTableBytes;
+    steps = reinterpret_cast<NgStep*>(tables);
+    ops = reinterpret_cast<NgOp*>(tables + kStepTableBytes);
+  }
+  // copies the tables of `prog` (all threads, before the CTA-wide barrier)
+  __device__ void load_tables(const NgProgram& prog) const {
+    const uint32_t* src_s = reinterpret_cast<const uint32_t*>(prog.steps);
+    const uint32_t* src_o = reinterpret_cast<const uint32_t*>(prog.ops);
+    uint32_t* dst_s = reinterpret_cast<uint32_t*>(steps);
+    uint32_t* dst_o = reinterpret_cast<uint32_t*>(ops);
+    for (uint32_t i = threadIdx.x; i < sizeof(NgStep) * (NG_MAX_OPS + 1) / 4; i += blockDim.x) dst_s[i] = src_s[i];
+    for (uint32_t i = threadIdx.x; i < sizeof(NgOp) * NG_MAX_OPS / 4; i += blockDim.x) dst_o[i] = src_o[i];
   }
   __device__ uint8_t* slab(int i) const { return base + (uint32_t)i * NB_SLAB_BYTES; }
   __device__ uint8_t* ring(int s) const { return ring_base + (uint32_t)s * NB_RING_STAGE_BYTES; }
@@ -119,7 +137,7 @@ __device__ __forceinline__ void producer_loop(const NgProgram& prog, const uint8
   uint32_t stage = 0, phase = 0;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     for (int k = 0; k < prog.n_ops; ++k) {
-      const NgOp& op = prog.ops[k];
+      const NgOp& op = sm.ops[k];
       const uint32_t bytes = (uint32_t)op.w_rows * 128u;
       for (int c = 0; c < op.n_chunks; ++c) {
         const uint8_t* src = wpack + (size_t)op.w_off[c] * 1024u;
@@ -146,7 +164,7 @@ __device__ __forceinline__ void mma_loop(const NgProgram& prog, const GarfSmem& 
   uint32_t stage = 0, phase = 0, g = 0;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     for (int k = 0; k < prog.n_ops; ++k, ++g) {
-      const NgOp& op = prog.ops[k];
+      const NgOp& op = sm.ops[k];
       const int n_chunks = op.n_chunks, n_blocks = op.n_blocks;
       uint32_t idesc[2], tcol[2], brow[2];
 #pragma unroll
@@ -195,7 +213,7 @@ __device__ __forceinline__ void stash_copier_loop(const NgProgram& prog, const G
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     uint8_t* tile_stash = stash + (size_t)tile * (size_t)slabs_per_tile * NB_SLAB_BYTES;
     for (int k = 0; k < prog.n_ops; ++k, ++g) {
-      const NgStep& st = prog.steps[k];
+      const NgStep& st = sm.steps[k];
       mbar_wait(&sm.in_ready[g & 1u], pair_parity(g));
       if (st.y_stash >= 0 && st.out_slab >= 0 && !(st.flags & NG_F_DIRECT)) {
         const int extra = (st.kind == NG_BSTEP_PLAIN && (st.flags & NG_F_SIGMA)) ? 1 : 0;
@@ -216,8 +234,8 @@ __device__ __forceinline__ void stash_copier_loop(const NgProgram& prog, const G
 // Range checks of a program before it reaches a kernel.
 inline int validate_garf_program(const NgProgram& prog, bool backward) {
   NB_CHECK_ARG(prog.n_ops >= 1 && prog.n_ops <= NG_MAX_OPS, "garf program: n_ops=%d", prog.n_ops);
-  NB_CHECK_ARG(prog.n_floats >= 0 && prog.n_floats <= NG_MAX_FLOATS, "garf program: %d packed floats (max %d)",
-               prog.n_floats, (int)NG_MAX_FLOATS);
+  NB_CHECK_ARG(prog.n_floats >= 0 && prog.n_floats <= (int)GarfSmem::kMaxProgramFloats,
+               "garf program: %d packed floats (max %d)", prog.n_floats, (int)GarfSmem::kMaxProgramFloats);
   for (int k = 0; k < prog.n_ops; ++k) {
     const NgOp& op = prog.ops[k];
     NB_CHECK_ARG(op.n_chunks >= 0 && op.n_chunks <= NG_MAX_CHUNKS, "garf op %d: n_chunks=%d", k, op.n_chunks);

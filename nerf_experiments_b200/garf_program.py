@@ -115,8 +115,8 @@ class _Builder:
     def finish(self, prog: NgProgram):
         if len(self.ops) > NG_MAX_OPS or len(self.steps) != len(self.ops) + 1:
             raise RuntimeError(f"GARF program: {len(self.ops)} ops / {len(self.steps)} steps")
-        if self.n_floats > NG_MAX_FLOATS:
-            raise RuntimeError(f"GARF program: {self.n_floats} packed floats exceed {NG_MAX_FLOATS}")
+        if self.n_floats > _lib.NG_MAX_PROGRAM_FLOATS:
+            raise RuntimeError(f"GARF program: {self.n_floats} packed floats exceed {_lib.NG_MAX_PROGRAM_FLOATS}")
         if self.steps[-1].wait_lag != 0:
             raise RuntimeError("GARF program: the last step must wait for the last op")
         prog.n_ops = len(self.ops)

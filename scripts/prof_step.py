@@ -13,7 +13,7 @@ dev = th.device("cuda:0")
 if which == "barf":
     from nerf_experiments_b200 import scene
     from nerf_experiments_b200.engine import TrainEngine
-    sc = scene.make_scene(bench.N_IMAGES, 200, 200, dev, rotation_noise=0.15, translation_noise=0.15, blur_sigmas=bench.BLUR_SIGMAS)
+    sc = scene.make_scene(bench.N_IMAGES, 48, 48, dev, rotation_noise=0.15, translation_noise=0.15, blur_sigmas=bench.BLUR_SIGMAS)
     model = bench.build_barf_model(sc, len(sc.batcher) // rays)
     eng = TrainEngine(model, dev, loss_fn=model.training_loss)
     g = th.Generator(device=dev).manual_seed(0)

@@ -115,4 +115,4 @@ def test_program_invariants():
                 op = prog.ops[k]
                 for c in range(op.n_chunks):
                     readers[op.a_slab[c]] = k
-    assert cg.fwd.n_floats <= _lib.NG_MAX_FLOATS and cg.bwd.n_floats <= _lib.NG_MAX_FLOATS
+    assert cg.fwd.n_floats <= _lib.NG_MAX_PROGRAM_FLOATS and cg.bwd.n_floats <= _lib.NG_MAX_PROGRAM_FLOATS
