@@ -210,7 +210,25 @@ class TrainEngine:
         if self.step_count < 1:
             raise RuntimeError("capture: run one eager step() with a batch of this shape first")
         self.coarse_weight = coarse_weight
-        self._static = [None if t is None else t.detach().clone() for t in batch]
+        # static inputs of the graph: views of ONE flat device buffer, so that a host batch arrives with a
+        # single host-to-device copy (`replay_packed`) instead of one copy per tensor
+        self._static_layout, off = [], 0
+        for t in batch:
+            if t is None:
+                self._static_layout.append(None)
+                continue
+            nbytes = t.numel() * t.element_size()
+            self._static_layout.append((off, nbytes, t.dtype, tuple(t.shape)))
+            off += (nbytes + 255) // 256 * 256
+        self._static_flat = th.zeros(max(off, 256), device=self.device, dtype=th.uint8)
+        self._static = []
+        for t, lay in zip(batch, self._static_layout):
+            if lay is None:
+                self._static.append(None)
+                continue
+            view = self._static_flat[lay[0]: lay[0] + lay[1]].view(lay[2]).view(lay[3])
+            view.copy_(t.detach())
+            self._static.append(view)
         from ._lib import launch_count
         import gc
         self.last_logs = None
@@ -246,6 +264,22 @@ class TrainEngine:
             restore()                             # capture does not execute; keep the engine state exact anyway
         th.cuda.current_stream(self.device).wait_stream(cs)
         return self
+
+    def replay_packed(self, host_flat: th.Tensor):
+        """One captured step on a batch that sits in ONE pinned host buffer laid out as `static_layout()`
+        says: a single host-to-device copy and a graph launch."""
+        self._pre_step()
+        self._static_flat.copy_(host_flat, non_blocking=True)
+        self._graph.replay()
+        self.step_count += 1
+        self.flat.version += 1
+        self.last_logs = self._static_logs
+        return self._static_logs["loss_fine"]
+
+    def static_layout(self):
+        """[(byte offset, bytes, dtype, shape) | None] of the captured batch inside the flat input buffer,
+        and the buffer's size in bytes."""
+        return list(self._static_layout), int(self._static_flat.numel())
 
     def release_graph(self):
         """Drops the captured graph. A graph that contains NCCL collectives keeps the communicator busy:
@@ -383,15 +417,50 @@ class HostStepper:
         self.count = 0
         self.read = 0
         self.h2d_bytes = 0
+        self._packed = None
+        self._packed_views = None
 
     def _read(self, slot: int) -> float:
         self.done[slot].synchronize()
         return float(self.loss_host[slot][0])
 
+    def _submit_packed(self, host_batch):
+        """Graph mode: the batch is packed into one pinned buffer per slot (host memcpy) and reaches the
+        graph's static inputs with ONE host-to-device copy on the compute stream; no copy stream, no
+        per-tensor copies, no device-to-device staging."""
+        n = self.depth + 1
+        s = self.count % n
+        eng = self.engine
+        compute = th.cuda.current_stream(eng.device)
+        layout, nbytes = eng.static_layout()
+        if self._packed is None:
+            self._packed = [th.zeros(nbytes, dtype=th.uint8).pin_memory() for _ in range(n)]
+            self._packed_views = [[None if lay is None else buf[lay[0]: lay[0] + lay[1]].view(lay[2]).view(lay[3])
+                                   for lay in layout] for buf in self._packed]
+        if self.done[s] is not None:
+            self.done[s].synchronize()                        # the copy that read this slot has long finished
+        for dst, src in zip(self._packed_views[s], host_batch):
+            if dst is not None:
+                dst.copy_(src)                                # host memcpy into the slot
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in host_batch if t is not None)
+        loss = eng.replay_packed(self._packed[s])
+        self.loss_host[s].copy_(loss.reshape(1), non_blocking=True)
+        ev = th.cuda.Event()
+        ev.record(compute)
+        self.done[s] = ev
+        self.count += 1
+        if self.count - self.read > self.depth:
+            out = self._read(self.read % n)
+            self.read += 1
+            return out
+        return None
+
     def submit(self, host_batch):
         n = self.depth + 1
         s = self.count % n
         eng = self.engine
+        if self.use_graph and eng._graph is not None:
+            return self._submit_packed(host_batch)
         compute = th.cuda.current_stream(eng.device)
         with th.cuda.stream(self.copy_stream):
             if self.done[s] is not None:

@@ -133,30 +133,35 @@ def test_host_stepper_matches_direct_steps(cuda):
     engine.step calls on the same batches, one call late."""
     from nerf_experiments_b200.engine import HostStepper, TrainEngine
     B = 96
-    batches = [_rays(B, 5, 30 + s) for s in range(5)]
+    batches = [_rays(B, 5, 30 + s) for s in range(7)]
     results = {}
-    for mode in ("direct", "host"):
-        model, cam = _build(cuda, True, 0, 32, seed=9)
+    for mode in ("direct", "host", "host_graph"):
+        # (no random sampling offsets: the graph and the eager steps must see the same rays)
+        model, cam = _build(cuda, True, 0, 32, seed=9, sampling="equidistant", offset=0.0)
         eng = TrainEngine(model, cuda)
         th.manual_seed(5)
         if mode == "direct":
             ls = [eng.step(*(t.to(cuda) for t in (o, d, target, idx, pw))).item() for (o, d, target, idx, pw) in batches]
         else:
-            st = HostStepper(eng)
+            # host_graph: run-ahead of two steps, the captured graph fed by ONE packed copy per step
+            st = HostStepper(eng) if mode == "host" else HostStepper(eng, depth=2, use_graph=True)
             ls = []
             for (o, d, target, idx, pw) in batches:
                 prev = st.submit(tuple(t.pin_memory() for t in (o, d, target, idx, pw)))
                 if prev is not None:
                     ls.append(prev)
-            ls.append(st.flush())
+            ls += st.drain()
             assert st.h2d_bytes == sum(t.numel() * t.element_size() for t in batches[0])
+            if mode == "host_graph":
+                assert eng._graph is not None and st._packed is not None
         results[mode] = (ls, eng.flat.flat.detach().clone())
-    assert len(results["host"][0]) == 5
-    assert results["direct"][0] == pytest.approx(results["host"][0], rel=1e-4)   # atomics: summation order varies
-    # gradients are flushed with floating-point atomics: equal up to summation order, which Adam's
-    # normalisation can blow up to a full lr-sized step for the odd parameter with a near-zero gradient
-    diff = (results["direct"][1] - results["host"][1]).abs()
-    assert float((diff > 2e-5).float().mean()) < 1e-3 and float(diff.max()) < 5 * 1e-3
+    for mode in ("host", "host_graph"):
+        assert len(results[mode][0]) == 7
+        assert results["direct"][0] == pytest.approx(results[mode][0], rel=1e-4)   # atomics: summation order varies
+        # gradients are flushed with floating-point atomics: equal up to summation order, which Adam's
+        # normalisation can blow up to a full lr-sized step for the odd parameter with a near-zero gradient
+        diff = (results["direct"][1] - results[mode][1]).abs()
+        assert float((diff > 2e-5).float().mean()) < 1e-3 and float(diff.max()) < 5 * 1e-3
 
 
 @pytest.mark.parametrize("B", [40, 300])
