@@ -276,6 +276,19 @@ class TrainEngine:
         self.last_logs = self._static_logs
         return self._static_logs["loss_fine"]
 
+    def pack_batch(self, batch, pin: bool = False) -> th.Tensor:
+        """The batch as one flat uint8 buffer in the layout of the graph's static inputs (on the device
+        of its tensors, or in pinned host memory for host tensors with `pin`): what `replay_packed` takes."""
+        layout, nbytes = self.static_layout()
+        first = next(t for t in batch if t is not None)
+        flat = th.zeros(nbytes, dtype=th.uint8, device=first.device)
+        if pin and not first.is_cuda:
+            flat = flat.pin_memory()
+        for t, lay in zip(batch, layout):
+            if lay is not None:
+                flat[lay[0]: lay[0] + lay[1]].view(lay[2]).view(lay[3]).copy_(t)
+        return flat
+
     def static_layout(self):
         """[(byte offset, bytes, dtype, shape) | None] of the captured batch inside the flat input buffer,
         and the buffer's size in bytes."""
