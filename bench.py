@@ -605,10 +605,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configurations / micro-benchmarks")
     args = ap.parse_args()
-    # defaults: 100 timed steps of ~3.3 ms for our arm (enough for ~10 clock samples), 3 steps of the
-    # bounded CPU sample for the reference arm
+    # defaults: 400 timed steps of ~3.5 ms for our arm in each of the two timed regions (~3 s under the
+    # clock sampler, whose nvidia-smi calls take ~0.3 s each), 3 steps for the reference arm
     if args.steps is None:
-        args.steps = 100 if args.impl == "ours" else 3
+        args.steps = 400 if args.impl == "ours" else 3
     if args.warmup is None:
         args.warmup = 10 if args.impl == "ours" else 1
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

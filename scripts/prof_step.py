@@ -13,7 +13,17 @@ dev = th.device("cuda:0")
 if which == "barf":
     from nerf_experiments_b200 import scene
     from nerf_experiments_b200.engine import TrainEngine
-    sc = scene.make_scene(bench.N_IMAGES, 48, 48, dev, rotation_noise=0.15, translation_noise=0.15, blur_sigmas=bench.BLUR_SIGMAS)
+    # random images / seeded poses instead of the sphere-traced scene: a profiler run should not spend
+    # its launch budget on ~17 000 scene-generation kernels
+    from types import SimpleNamespace
+    from nerf_experiments_b200.ray_batcher import GpuRayBatcher
+    gcpu = th.Generator().manual_seed(0)
+    c2w = scene.look_at_poses(bench.N_IMAGES, 4.0, gcpu)
+    noisy = c2w.clone()
+    noisy[:, :3, 3] += 0.1 * th.randn((bench.N_IMAGES, 3), generator=gcpu)
+    batcher = GpuRayBatcher(th.rand((bench.N_IMAGES, 64, 64, len(bench.BLUR_SIGMAS), 3), generator=gcpu), c2w,
+                            64 / 2 / 0.36, noisy, bench.BLUR_SIGMAS, device=dev)
+    sc = SimpleNamespace(batcher=batcher, n_images=bench.N_IMAGES)
     model = bench.build_barf_model(sc, len(sc.batcher) // rays)
     eng = TrainEngine(model, dev, loss_fn=model.training_loss)
     g = th.Generator(device=dev).manual_seed(0)
