@@ -310,3 +310,53 @@ def test_garf_training_step_reduces_loss(cuda):
     target = th.full((256, 3), 0.25, device=cuda)
     losses = [float(m.training_step((o, d, target), i)) for i in range(30)]
     assert np.isfinite(losses).all() and np.mean(losses[-5:]) < np.mean(losses[:5])
+
+
+def test_garf_camera_calibration_engine_matches_torch_optimisers(cuda):
+    """garf/model_camera_calibration.py: 6-tuple batches, poses refined in front of the fused field; the
+    engine's single fused Adam over five groups == the reference-shaped step with three optimisers."""
+    from nerf_experiments_b200.model_garf import garf_engine
+    from nerf_experiments_b200.model_garf_camera_calibration import CameraCalibrationModel
+    B, n_img = 192, 6
+    gen = th.Generator().manual_seed(3)
+    batches = []
+    for _ in range(5):
+        o = th.nn.functional.normalize(th.randn((B, 3), generator=gen), dim=1) * 4.0
+        d = th.nn.functional.normalize(-o + 0.3 * th.randn((B, 3), generator=gen), dim=1)
+        o_n = o + 0.05 * th.randn((B, 3), generator=gen)
+        d_n = th.nn.functional.normalize(d + 0.05 * th.randn((B, 3), generator=gen), dim=1)
+        idx = th.randint(0, n_img, (B,), generator=gen)
+        batches.append(tuple(x.to(cuda) for x in (o, o_n, d, d_n, th.rand((B, 3), generator=gen), idx,
+                                                  th.rand(B, generator=gen), th.rand(B, generator=gen))))
+    out = {}
+    for mode in ("torch", "engine", "graph"):
+        th.manual_seed(5)
+        m = CameraCalibrationModel(n_img, 1e-3, 1e-5, 40, 10, 2.0, 7.0, 16, 32, 0.5, 1.5, 2.0,
+                                   1e-3, 1e-4, 50, 0.0, 2e-3, 1e-4, 60, 0.0).to(cuda)
+        m.train()
+        assert len(m.param_groups) == 5
+        losses = []
+        if mode == "torch":
+            for i, b in enumerate(batches):
+                losses.append(float(m.training_step(b[:6], i, u_rays=(b[6], b[7]))))
+            flat = th.cat([p.detach().reshape(-1) for g in m.param_groups for p in g["parameters"]])
+        else:
+            eng = garf_engine(m, cuda)
+            eng.step(*batches[0])
+            losses.append(float(eng.last_logs["loss_fine"] + eng.last_logs["train_proposal_loss"]))
+            if mode == "graph":
+                eng.capture(*batches[0])
+            for b in batches[1:]:
+                (eng.replay if mode == "graph" else eng.step)(*b)
+                losses.append(float(eng.last_logs["loss_fine"] + eng.last_logs["train_proposal_loss"]))
+            flat = eng.flat.flat.detach().clone()
+            eng.release_graph()
+        out[mode] = (losses, flat)
+        poses = th.cat([p.detach().reshape(-1) for p in m.camera_extrinsics.parameters()])
+        assert float(poses.abs().max()) > 1e-4            # the poses moved
+    for mode in ("engine", "graph"):
+        assert out[mode][0] == pytest.approx(out["torch"][0], rel=2e-3)
+        diff = (out[mode][1] - out["torch"][1]).abs()
+        assert float((diff > 5e-5).float().mean()) < 2e-3 and float(diff.max()) < 2e-2
+        # the pose group itself (last 36 floats): Adam's first steps move every element by ~lr
+        assert th.allclose(out[mode][1][-6 * n_img:], out["torch"][1][-6 * n_img:], atol=3e-4)
