@@ -70,6 +70,8 @@ garf_bwd_kernel(const __grid_constant__ GarfBwdParams p) {
     const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t off0 = (uint32_t)row * 128u + ((uint32_t)((2 * cq) ^ (row & 7)) << 4);
     const uint32_t off1 = (uint32_t)row * 128u + ((uint32_t)((2 * cq + 1) ^ (row & 7)) << 4);
+    const uint32_t sec_off = off0 < off1 ? off0 : off1;   // the 32-byte sector holding both chunks
+    const bool odd_row = (row & 1) != 0;
     const uint32_t slab_base = smem_u32(sm.slab(0));
     const bool want = p.want_input_grads != 0;
     RowSync rs;
@@ -110,14 +112,13 @@ garf_bwd_kernel(const __grid_constant__ GarfBwdParams p) {
         const int kind = st.kind, nsl = st.n_slabs, flags = st.flags;
         // the forward's pre-activations of this layer: requested before the accumulator is waited for
         // (two 64-column groups in flight; the next two are requested while these are consumed)
-        uint4 zq[2][2];
+        Sector32 zq[2];
         const uint8_t* zbase = ztile + (size_t)(st.z_stash < 0 ? 0 : st.z_stash) * NB_SLAB_BYTES;
         if (kind == NG_BSTEP_ACT) {
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
             if (j < nsl) {
-              zq[j][0] = ldg128_stream(zbase + (size_t)j * NB_SLAB_BYTES + off0);
-              zq[j][1] = ldg128_stream(zbase + (size_t)j * NB_SLAB_BYTES + off1);
+              zq[j] = ldg256_stream(zbase + (size_t)j * NB_SLAB_BYTES + sec_off);
             }
           }
         }
@@ -171,12 +172,10 @@ garf_bwd_kernel(const __grid_constant__ GarfBwdParams p) {
           uint32_t va[16], vb[16];
           auto group = [&](const uint32_t (&v)[16], int j) {
             uint32_t dp[8];
-            const uint32_t zz[8] = {zq[j & 1][0].x, zq[j & 1][0].y, zq[j & 1][0].z, zq[j & 1][0].w,
-                                    zq[j & 1][1].x, zq[j & 1][1].y, zq[j & 1][1].z, zq[j & 1][1].w};
-            if (j + 2 < nsl) {     // the slot is free again: request the group after the next
-              zq[j & 1][0] = ldg128_stream(zbase + (size_t)(j + 2) * NB_SLAB_BYTES + off0);
-              zq[j & 1][1] = ldg128_stream(zbase + (size_t)(j + 2) * NB_SLAB_BYTES + off1);
-            }
+            uint32_t zz[8];
+            unswap_row(zq[j & 1], odd_row, zz);
+            if (j + 2 < nsl)       // the slot is free again: request the group after the next
+              zq[j & 1] = ldg256_stream(zbase + (size_t)(j + 2) * NB_SLAB_BYTES + sec_off);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const float4 c = coef4[16 * j + q];
@@ -211,8 +210,7 @@ garf_bwd_kernel(const __grid_constant__ GarfBwdParams p) {
             }
             if (direct) {
               uint8_t* ds = dytile + (size_t)(st.y_stash + j) * NB_SLAB_BYTES;
-              stg128(ds + off0, dp[0], dp[1], dp[2], dp[3]);
-              stg128(ds + off1, dp[4], dp[5], dp[6], dp[7]);
+              stg256_row(ds + sec_off, odd_row, dp);
             } else {
               const uint32_t sb = slab_base + (uint32_t)(st.out_slab + j) * NB_SLAB_BYTES;
               sts128g(sb + off0, dp[0], dp[1], dp[2], dp[3]);

@@ -63,6 +63,8 @@ garf_fwd_kernel(const __grid_constant__ GarfFwdParams p) {
     const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t off0 = (uint32_t)row * 128u + ((uint32_t)((2 * cq) ^ (row & 7)) << 4);       // this thread's two
     const uint32_t off1 = (uint32_t)row * 128u + ((uint32_t)((2 * cq + 1) ^ (row & 7)) << 4);   // 16-byte chunks of a slab
+    const uint32_t sec_off = off0 < off1 ? off0 : off1;   // the 32-byte sector holding both chunks
+    const bool odd_row = (row & 1) != 0;
     const uint32_t slab_base = smem_u32(sm.slab(0));
     RowSync rs;
     uint32_t g0 = 0;
@@ -90,13 +92,13 @@ garf_fwd_kernel(const __grid_constant__ GarfFwdParams p) {
         const uint32_t pd0 = cq == 0 ? pack_bf16(md.x, md.y) : 0u, pd1 = cq == 0 ? pack_bf16(md.z, 0.f) : 0u;
         if (prog.aux_pos_stash >= 0) {
           uint8_t* s = ytile + (size_t)prog.aux_pos_stash * NB_SLAB_BYTES;
-          stg128(s + off0, px0, px1, 0u, 0u);
-          stg128(s + off1, 0u, 0u, 0u, 0u);
+          const uint32_t a[8] = {px0, px1, 0u, 0u, 0u, 0u, 0u, 0u};
+          stg256_row(s + sec_off, odd_row, a);
         }
         if (prog.aux_dir_stash >= 0) {
           uint8_t* s = ytile + (size_t)prog.aux_dir_stash * NB_SLAB_BYTES;
-          stg128(s + off0, pd0, pd1, 0u, 0u);
-          stg128(s + off1, 0u, 0u, 0u, 0u);
+          const uint32_t a[8] = {pd0, pd1, 0u, 0u, 0u, 0u, 0u, 0u};
+          stg256_row(s + sec_off, odd_row, a);
         }
       }
 
@@ -208,8 +210,7 @@ garf_fwd_kernel(const __grid_constant__ GarfFwdParams p) {
             for (int j = 0; j < 4; ++j) {
               if (j < nsl) {
                 uint8_t* zs = ztile + (size_t)(st.z_stash + j) * NB_SLAB_BYTES;
-                stg128(zs + off0, zp[j][0], zp[j][1], zp[j][2], zp[j][3]);
-                stg128(zs + off1, zp[j][4], zp[j][5], zp[j][6], zp[j][7]);
+                stg256_row(zs + sec_off, odd_row, zp[j]);
               }
             }
           }

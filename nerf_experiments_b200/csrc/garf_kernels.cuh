@@ -125,7 +125,7 @@ struct RowSync {
 
 // publish step g: shared-memory writes -> async proxy, accumulator reads ordered before the next MMAs
 __device__ __forceinline__ void publish_step(const GarfSmem& sm, uint32_t g, bool wrote_smem, int lane) {
-  if (wrote_smem) fence_proxy_async();
+  if (wrote_smem) writer_proxy_fence();
   tcgen05_fence_before();
   __syncwarp();
   if (lane == 0) mbar_arrive(&sm.in_ready[g & 1u]);
@@ -176,6 +176,7 @@ __device__ __forceinline__ void mma_loop(const NgProgram& prog, const GarfSmem& 
       }
       uint32_t acc = op.accumulate ? 1u : 0u;
       mbar_wait(&sm.in_ready[g & 1u], pair_parity(g));
+      consumer_proxy_fence();
       tcgen05_fence_after();
       for (int c = 0; c < n_chunks; ++c) {
         const uint32_t a_lo = slab0 + (uint32_t)op.a_slab[c] * (NB_SLAB_BYTES >> 4);
@@ -215,6 +216,7 @@ __device__ __forceinline__ void stash_copier_loop(const NgProgram& prog, const G
     for (int k = 0; k < prog.n_ops; ++k, ++g) {
       const NgStep& st = sm.steps[k];
       mbar_wait(&sm.in_ready[g & 1u], pair_parity(g));
+      consumer_proxy_fence();
       if (st.y_stash >= 0 && st.out_slab >= 0 && !(st.flags & NG_F_DIRECT)) {
         const int extra = (st.kind == NG_BSTEP_PLAIN && (st.flags & NG_F_SIGMA)) ? 1 : 0;
         const int n = st.n_slabs + extra;
@@ -282,6 +284,32 @@ __device__ __forceinline__ void sts128g(uint32_t addr, uint32_t a, uint32_t b, u
 __device__ __forceinline__ void stg128(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d)
                : "memory");
+}
+// A row thread's two 16-byte chunks of a slab row — (2cq) ^ (row & 7) and its neighbour — are the two
+// halves of ONE 32-byte sector: a single 256-bit access instead of two scattered 128-bit ones (with a
+// lane per row every access is its own L1 transaction, and the row warps' global accesses are bound
+// by the number of those). On odd rows the halves are swapped. `sec` = the sector's address.
+__device__ __forceinline__ void stg256_row(void* sec, bool odd, const uint32_t (&v)[8]) {
+  asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(sec),
+               "r"(odd ? v[4] : v[0]), "r"(odd ? v[5] : v[1]), "r"(odd ? v[6] : v[2]), "r"(odd ? v[7] : v[3]),
+               "r"(odd ? v[0] : v[4]), "r"(odd ? v[1] : v[5]), "r"(odd ? v[2] : v[6]), "r"(odd ? v[3] : v[7])
+               : "memory");
+}
+// raw sector (halves in memory order); `unswap_row` restores the logical order
+struct Sector32 { uint32_t w[8]; };
+__device__ __forceinline__ Sector32 ldg256_stream(const void* sec) {
+  Sector32 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+               : "l"(sec));
+  return r;
+}
+__device__ __forceinline__ void unswap_row(const Sector32& s, bool odd, uint32_t (&v)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[i] = odd ? s.w[4 + i] : s.w[i];
+    v[4 + i] = odd ? s.w[i] : s.w[4 + i];
+  }
 }
 __device__ __forceinline__ uint4 ldg128_stream(const void* p) {
   uint4 r;

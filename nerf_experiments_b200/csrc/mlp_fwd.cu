@@ -243,7 +243,7 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdParams p) {
             sign_bits[j] = bits;    // stored after the last slab has been published: a global store in
                                     // flight makes the proxy fence (MEMBAR.ALL.CTA) wait for its ack
             NB_TRACE(ts + 2, tr);
-            fence_proxy_async();
+            writer_proxy_fence();
             NB_TRACE(ts + 3, tr);
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.slab_ready[j]);

@@ -233,7 +233,7 @@ struct DrainBits {
 
 // publish one slab: proxy fence, then one arrival per warp
 __device__ __forceinline__ void signal_slab(uint64_t* slab_ready, int s, int lane) {
-  tc::fence_proxy_async();
+  tc::writer_proxy_fence();
   __syncwarp();
   if (lane == 0) tc::mbar_arrive(&slab_ready[s]);
 }
@@ -246,7 +246,7 @@ __device__ __forceinline__ void warp_mbar_wait(uint64_t* bar, uint32_t parity, i
 
 // Row warps: publish the slabs in `mask` (generic-proxy writes -> async proxy, one arrival per warp).
 __device__ __forceinline__ void signal_slabs(const uint64_t* slab_ready, uint32_t mask, int lane) {
-  tc::fence_proxy_async();
+  tc::writer_proxy_fence();
   __syncwarp();
   if (lane == 0) {
     while (mask) {
@@ -448,6 +448,7 @@ __device__ __forceinline__ void mma_issuer_loop(const NbProgram& prog, const Til
         const int n_sub = op.n_sub[c];
         const uint32_t sub_stride = (uint32_t)op.w_rows[c] * 8u;   // image rows * 128 B >> 4
         for (int sub = 0; sub < n_sub; ++sub) trk.acquire(sm.slab_ready, op.a_src[c] + sub);
+        tc::consumer_proxy_fence();
         NB_TRACE(128 + oi * 8 + c, elected && oi < 16 && c < 8);
         tc::mbar_wait(&sm.full[stage], phase);
         NB_TRACE(256 + oi * 8 + c, elected && oi < 16 && c < 8);
@@ -532,6 +533,7 @@ __device__ __forceinline__ void stash_loop(const NbProgram& prog, const TileSche
           const int s = __ffs(m) - 1;
           m &= m - 1u;
           trk.acquire(sm.slab_ready, s);
+          tc::consumer_proxy_fence();
           const int d = dst_of(ph, s);
           if (d >= 0) {
             tc::bulk_s2g(tile_stash + (size_t)d * NB_SLAB_BYTES, sm.slab(s), NB_SLAB_BYTES);

@@ -80,6 +80,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+// Where the generic-proxy -> async-proxy fence of a slab publication is executed. Writer side (default
+// off): every row warp fences before its mbarrier arrival — the fence is a MEMBAR.ALL.CTA, which also
+// waits for the warp's global stores in flight. Consumer side (NB_CONSUMER_FENCE): the row warps only
+// release-arrive; the ONE thread that issues the async-proxy reads (MMA issuer / stash copier) fences
+// after it has acquired the barrier phase (the writes are then ordered before the fence in causality
+// order, the async operations after it in program order).
+#ifdef NB_CONSUMER_FENCE
+__device__ __forceinline__ void writer_proxy_fence() {}
+__device__ __forceinline__ void consumer_proxy_fence() { fence_proxy_async(); }
+#else
+__device__ __forceinline__ void writer_proxy_fence() { fence_proxy_async(); }
+__device__ __forceinline__ void consumer_proxy_fence() {}
+#endif
 __device__ __forceinline__ void tcgen05_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
