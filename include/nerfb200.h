@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NERFB200_ABI_VERSION 3   /* 3: adam_step_dev replaces adam_step_sched; GARF fused field; render_rays; trans_cdf / prop_loss */
+#define NERFB200_ABI_VERSION 4   /* 3: adam_step_dev replaces adam_step_sched; GARF fused field; render_rays; trans_cdf / prop_loss. 4: NbWgradItem z duty */
 
 enum {
   NERFB200_OK = 0,

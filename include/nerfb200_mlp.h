@@ -174,12 +174,19 @@ typedef struct {
   int32_t bias_dst;             /* float index of the bias gradient of output feature m0 (the */
                                 /* column sums of the dY slabs, += over the tile range), -1:  */
                                 /* another item of the same dY slabs carries it               */
-  int32_t mode;                 /* NB_WGRAD_MMA, or NB_WGRAD_COLSUM: no weight block — x_slab  */
-                                /* then indexes the Z stash (pre-activations of a Gaussian    */
-                                /* layer, n_x_slabs == n_dy_slabs) and the item reduces        */
-                                /* sum dz (bias) and sum z*dz (Gaussian width) per column      */
-  int32_t coef_dst;             /* COLSUM: float index of the inverse-std parameter (and of   */
+  int32_t mode;                 /* NB_WGRAD_MMA, or NB_WGRAD_COLSUM: no weight block, only the */
+                                /* column sums of the z duty below                             */
+  int32_t coef_dst;             /* z duty: float index of the inverse-std parameter (and of   */
                                 /* its gradient) of output feature m0, -1: none               */
+  /* "z duty" (GARF): the item also streams n_z_slabs slabs of the Z stash (pre-activations of a      */
+  /* Gaussian layer) — z slab j belongs to the item's dY slab z_first + j — and reduces, for those    */
+  /* dY slabs, sum dz (bias gradient, at zbias_dst) and sum z*dz (Gaussian width, at coef_dst) per    */
+  /* column while the slabs sit in shared memory for the MMAs. 2*ceil(n_dy/2) + n_x + n_z <= 9.       */
+  /* NB_WGRAD_COLSUM items are z duty without a weight block: n_x_slabs = 0, n_z_slabs = n_dy_slabs.  */
+  int32_t z_slab;               /* first slab inside a tile's Z stash, -1: no z duty          */
+  int32_t n_z_slabs;            /* 0..4                                                        */
+  int32_t z_first;              /* index (within the item) of the dY slab of z slab 0          */
+  int32_t zbias_dst;            /* float index of the bias gradient of output feature m0, -1   */
 } NbWgradItem;
 enum { NB_WGRAD_MMA = 0, NB_WGRAD_COLSUM = 1 };
 

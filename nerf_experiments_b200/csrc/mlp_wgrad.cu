@@ -11,6 +11,10 @@
 // Bias gradients ride along: the four flush warps are idle while an item accumulates, so each
 // sums the columns of one dY half slab per pipeline stage while it sits in shared memory (the
 // item that carries bias_dst >= 0 for its dY slabs), fp32 in registers over the whole item.
+// GARF's Gaussian-width gradients (sum over samples of z * dz) ride the same way: an item with
+// "z duty" also streams the z slabs of some of its dY slabs into the stage (a stage holds up to
+// nine half slabs: dY | X | Z), so the dz slabs are read from HBM once for the weight block AND
+// the column sums; column-sum-only items (no weight block) take what does not fit.
 #include "common.cuh"
 #include "mlp.h"
 #include "tc.cuh"
@@ -24,7 +28,8 @@ constexpr int kWgThreads = 192;
 constexpr int kWgStages = 3;
 constexpr int kHalfRows = 64;                         // samples per pipeline stage
 constexpr uint32_t kHalfSlabBytes = kHalfRows * 128;  // 8 KB
-constexpr uint32_t kStageBytes = 8 * kHalfSlabBytes;  // up to 4 dY + 4 X half slabs
+constexpr int kStageHalfSlabs = 9;                    // dY (2 per 128-feature block) | X | Z, packed in that order
+constexpr uint32_t kStageBytes = kStageHalfSlabs * kHalfSlabBytes;
 constexpr uint32_t kWgSmemBytes = kWgStages * kStageBytes + 256;
 
 struct WgradParams {
@@ -72,12 +77,14 @@ mlp_wgrad_kernel(const __grid_constant__ WgradParams p) {
       uint32_t stage = 0, phase = 0;
       for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
         const NbWgradItem item = p.items[it];
-        const uint32_t bytes = (uint32_t)(item.n_dy_slabs + item.n_x_slabs) * kHalfSlabBytes;
+        const int n_x = item.mode == NB_WGRAD_COLSUM ? 0 : item.n_x_slabs;
+        const int n_z = item.z_slab >= 0 ? item.n_z_slabs : 0;
+        const int pos_x = 2 * ((item.n_dy_slabs + 1) / 2), pos_z = pos_x + n_x;
+        const uint32_t bytes = (uint32_t)(item.n_dy_slabs + n_x + n_z) * kHalfSlabBytes;
         for (int tile = item.tile_begin; tile < item.tile_end; ++tile) {
           const uint8_t* dy = p.dy_stash + ((size_t)tile * p.dy_slabs_per_tile + item.dy_slab) * NB_SLAB_BYTES;
-          const uint8_t* x = item.mode == NB_WGRAD_COLSUM
-              ? p.z_stash + ((size_t)tile * p.z_slabs_per_tile + item.x_slab) * NB_SLAB_BYTES
-              : p.x_stash + ((size_t)tile * p.x_slabs_per_tile + item.x_slab) * NB_SLAB_BYTES;
+          const uint8_t* x = p.x_stash + ((size_t)tile * p.x_slabs_per_tile + item.x_slab) * NB_SLAB_BYTES;
+          const uint8_t* z = p.z_stash + ((size_t)tile * p.z_slabs_per_tile + (n_z ? item.z_slab : 0)) * NB_SLAB_BYTES;
           for (int half = 0; half < 2; ++half) {
             mbar_wait(&empty[stage], phase ^ 1u);
             mbar_arrive_expect_tx(&full[stage], bytes);
@@ -85,8 +92,11 @@ mlp_wgrad_kernel(const __grid_constant__ WgradParams p) {
             for (int s = 0; s < item.n_dy_slabs; ++s)
               bulk_g2s(dst + s * kHalfSlabBytes, dy + (size_t)s * NB_SLAB_BYTES + half * kHalfSlabBytes,
                        kHalfSlabBytes, &full[stage]);
-            for (int s = 0; s < item.n_x_slabs; ++s)
-              bulk_g2s(dst + (4 + s) * kHalfSlabBytes, x + (size_t)s * NB_SLAB_BYTES + half * kHalfSlabBytes,
+            for (int s = 0; s < n_x; ++s)
+              bulk_g2s(dst + (pos_x + s) * kHalfSlabBytes, x + (size_t)s * NB_SLAB_BYTES + half * kHalfSlabBytes,
+                       kHalfSlabBytes, &full[stage]);
+            for (int s = 0; s < n_z; ++s)
+              bulk_g2s(dst + (pos_z + s) * kHalfSlabBytes, z + (size_t)s * NB_SLAB_BYTES + half * kHalfSlabBytes,
                        kHalfSlabBytes, &full[stage]);
             if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
           }
@@ -111,6 +121,7 @@ mlp_wgrad_kernel(const __grid_constant__ WgradParams p) {
           continue;
         }
         const int n_mb = (item.n_dy_slabs + 1) / 2;
+        const uint32_t pos_x = 2u * (uint32_t)n_mb;
         const uint32_t idesc = umma_idesc(128, item.n_x_slabs * 64, true, true);
         if (flush_pending) {   // the flush of the previous MMA item must have drained TMEM
           mbar_wait(acc_empty, e_phase);
@@ -125,7 +136,7 @@ mlp_wgrad_kernel(const __grid_constant__ WgradParams p) {
             tcgen05_fence_after();
             const uint32_t base = smem_u32(smem + stage * kStageBytes);
             for (int k = 0; k < kHalfRows / 16; ++k) {
-              const uint64_t bdesc = umma_desc_mnmajor(base + 4 * kHalfSlabBytes, kHalfSlabBytes, k);
+              const uint64_t bdesc = umma_desc_mnmajor(base + pos_x * kHalfSlabBytes, kHalfSlabBytes, k);
               for (int mb = 0; mb < n_mb; ++mb) {
                 const uint64_t adesc = umma_desc_mnmajor(base + mb * 2 * kHalfSlabBytes, kHalfSlabBytes, k);
                 umma(tmem_base + (uint32_t)(mb * 256), adesc, bdesc, idesc, acc);
@@ -149,7 +160,11 @@ mlp_wgrad_kernel(const __grid_constant__ WgradParams p) {
       const NbWgradItem item = p.items[it];
       const int n_mb = (item.n_dy_slabs + 1) / 2;
       const bool colsum = item.mode == NB_WGRAD_COLSUM;
-      const bool sums = (item.bias_dst >= 0 || (colsum && item.coef_dst >= 0)) && warp < item.n_dy_slabs;
+      // z duty of this warp's dY slab: bias and Gaussian-width sums
+      const bool zduty = item.z_slab >= 0 && warp >= item.z_first && warp < item.z_first + item.n_z_slabs &&
+                         warp < item.n_dy_slabs;
+      const bool sums = (item.bias_dst >= 0 && warp < item.n_dy_slabs) || zduty;
+      const uint32_t z_pos = 2u * (uint32_t)n_mb + (colsum ? 0u : (uint32_t)item.n_x_slabs) + (uint32_t)(warp - item.z_first);
       float bacc[8][8], zacc[8][8];
 #pragma unroll
       for (int q = 0; q < 8; ++q)
@@ -159,8 +174,9 @@ mlp_wgrad_kernel(const __grid_constant__ WgradParams p) {
         for (int half = 0; half < 2; ++half) {
           mbar_wait(&full[stage], phase);
           if (sums) {
-            const uint8_t* base = smem + stage * kStageBytes + (uint32_t)warp * kHalfSlabBytes +
-                                  (uint32_t)(rg * 16) * 128u + (uint32_t)pc * 16u;
+            const uint32_t lane_off = (uint32_t)(rg * 16) * 128u + (uint32_t)pc * 16u;
+            const uint8_t* base = smem + stage * kStageBytes + (uint32_t)warp * kHalfSlabBytes + lane_off;
+            const uint8_t* zbase = smem + stage * kStageBytes + (zduty ? z_pos : 0u) * kHalfSlabBytes + lane_off;
 #pragma unroll
             for (int r8 = 0; r8 < 2; ++r8) {
 #pragma unroll
@@ -170,8 +186,8 @@ mlp_wgrad_kernel(const __grid_constant__ WgradParams p) {
                 bacc[q][2] += __uint_as_float(v.y << 16); bacc[q][3] += __uint_as_float(v.y & 0xffff0000u);
                 bacc[q][4] += __uint_as_float(v.z << 16); bacc[q][5] += __uint_as_float(v.z & 0xffff0000u);
                 bacc[q][6] += __uint_as_float(v.w << 16); bacc[q][7] += __uint_as_float(v.w & 0xffff0000u);
-                if (colsum) {   // Gaussian width gradient: sum over samples of z * dz (same slab position in the z stash)
-                  const uint4 z = *reinterpret_cast<const uint4*>(base + 4u * kHalfSlabBytes + (uint32_t)(r8 * 8 + q) * 128u);
+                if (zduty) {   // Gaussian width gradient: sum over samples of z * dz (same position in the z slab)
+                  const uint4 z = *reinterpret_cast<const uint4*>(zbase + (uint32_t)(r8 * 8 + q) * 128u);
                   zacc[q][0] = fmaf(__uint_as_float(z.x << 16), __uint_as_float(v.x << 16), zacc[q][0]);
                   zacc[q][1] = fmaf(__uint_as_float(z.x & 0xffff0000u), __uint_as_float(v.x & 0xffff0000u), zacc[q][1]);
                   zacc[q][2] = fmaf(__uint_as_float(z.y << 16), __uint_as_float(v.y << 16), zacc[q][2]);
@@ -204,14 +220,15 @@ mlp_wgrad_kernel(const __grid_constant__ WgradParams p) {
           tot[e] += __shfl_xor_sync(0xffffffffu, tot[e], 8);
           tot[e] += __shfl_xor_sync(0xffffffffu, tot[e], 16);
         }
-        if (rg == 0 && item.tile_end > item.tile_begin && item.bias_dst >= 0) {
+        const int bias_dst = zduty ? item.zbias_dst : item.bias_dst;
+        if (rg == 0 && item.tile_end > item.tile_begin && bias_dst >= 0) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int m = warp * 64 + pc * 8 + e;
-            if (m < item.m_real) atomicAdd(p.d_params + item.bias_dst + m, tot[e]);
+            if (m < item.m_real) atomicAdd(p.d_params + bias_dst + m, tot[e]);
           }
         }
-        if (colsum && item.coef_dst >= 0) {
+        if (zduty && item.coef_dst >= 0) {
           float zt[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) zt[e] = zacc[0][e];

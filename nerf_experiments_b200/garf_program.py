@@ -191,13 +191,46 @@ def _mma_bwd(b: _Builder, lin: Linear, a_slabs, k_outs, in0, n_in, tmem_col, acc
     b.op(a_slabs, k16s, offs, n_pad, [(tmem_col, n_pad, 0)], accumulate)
 
 
+WGRAD_STAGE_HALF_SLABS = 9      # csrc/mlp_wgrad.cu: half slabs of one pipeline stage
+
+
 def _colsum_units(units, dy0, z0, layer: GaussLinear):
-    n_out = layer.lin.out_f
-    for u in range(_ceil(n_out, 256)):
-        m = min(256, n_out - 256 * u)
-        units.append(WgradUnit(dy0 + 4 * u, _ceil(m, 64), z0 + 4 * u, _ceil(m, 64), m, 0, 0, 0,
-                               bias_dst=layer.lin.b_off + 256 * u, mode=_lib.WGRAD_COLSUM,
-                               coef_dst=layer.g_off + 256 * u))
+    """Bias and Gaussian-width gradients of one layer (sum dz, sum z*dz per column): a "z duty" that rides on
+    the weight units already streaming the layer's dz slabs wherever their pipeline stage has room for
+    the z slabs (2*ceil(n_dy/2) + n_x + n_z <= 9 half slabs); what is left becomes column-sum-only units.
+    Must be called after the layer's weight units have been appended."""
+    n_slabs = _ceil(layer.lin.out_f, 64)
+    todo = [True] * n_slabs                       # dz slab dy0 + s still needs its sums
+    for u in units:
+        if u.mode != _lib.WGRAD_MMA or u.n_z_slabs or u.bias_dst >= 0:
+            continue
+        lo, hi = u.dy_slab - dy0, u.dy_slab - dy0 + u.n_dy_slabs
+        if lo < 0 or hi > n_slabs:
+            continue
+        room = WGRAD_STAGE_HALF_SLABS - 2 * _ceil(u.n_dy_slabs, 2) - u.n_x_slabs
+        run = [s for s in range(lo, hi) if todo[s]]
+        if room <= 0 or not run:
+            continue
+        first = run[0]
+        n = 0
+        while n < room and first + n < hi and todo[first + n]:
+            n += 1
+        for s in range(first, first + n):
+            todo[s] = False
+        u.z_slab, u.n_z_slabs, u.z_first = z0 + first, n, first - lo
+        u.zbias_dst, u.coef_dst = layer.lin.b_off + 64 * lo, layer.g_off + 64 * lo
+    s = 0
+    while s < n_slabs:
+        if not todo[s]:
+            s += 1
+            continue
+        n = 1
+        while n < 4 and s + n < n_slabs and todo[s + n]:
+            n += 1
+        m = min(64 * n, layer.lin.out_f - 64 * s)
+        units.append(WgradUnit(dy0 + s, n, 0, 0, m, 0, 0, 0, mode=_lib.WGRAD_COLSUM, coef_dst=layer.g_off + 64 * s,
+                               z_slab=z0 + s, n_z_slabs=n, z_first=0, zbias_dst=layer.lin.b_off + 64 * s))
+        s += n
 
 
 def _weight_units(units, lin: Linear, dy0, n_out, x0, in0, n_in, bias=False, out0=0):

@@ -295,8 +295,12 @@ class WgradUnit:
     dst: int
     ld: int
     bias_dst: int = -1     # float index of the bias gradient of the unit's first output feature
-    mode: int = 0          # _lib.WGRAD_MMA | _lib.WGRAD_COLSUM (x_slab then indexes the z stash)
-    coef_dst: int = -1     # COLSUM: float index of the Gaussian inverse-std parameter of the first feature
+    mode: int = 0          # _lib.WGRAD_MMA | _lib.WGRAD_COLSUM (no weight block: n_x_slabs == 0, z duty only)
+    coef_dst: int = -1     # z duty: float index of the Gaussian inverse-std parameter of the first feature
+    z_slab: int = -1       # z duty (include/nerfb200_mlp.h): first z stash slab, count, first dY slab it belongs to,
+    n_z_slabs: int = 0     # float index of the bias gradient of the first feature
+    z_first: int = 0
+    zbias_dst: int = -1
 
 
 @dataclass
@@ -490,10 +494,13 @@ def schedule_wgrad(units: List[WgradUnit], n_tiles: int, n_workers: int):
     import os
     from ._lib import NbWgradItem
     per_worker = float(os.environ.get("NB_WGRAD_ITEMS_PER_WORKER", "3"))   # the env knob is for experiments
-    cost = [(u.n_dy_slabs + u.n_x_slabs) for u in units]
+    cost = [(u.n_dy_slabs + u.n_x_slabs + u.n_z_slabs) for u in units]
     total = sum(cost) * n_tiles
     target = max(total / max(per_worker * n_workers, 1), 1.0)
     items = []
+    for u in units:     # one pipeline stage of csrc/mlp_wgrad.cu holds nine half slabs: dY (pairs) | X | Z
+        if 2 * ((u.n_dy_slabs + 1) // 2) + u.n_x_slabs + u.n_z_slabs > 9 or not (1 <= u.n_dy_slabs <= 4) or u.n_x_slabs > 4:
+            raise RuntimeError(f"weight-gradient unit does not fit a pipeline stage: {u}")
     for u, c in zip(units, cost):
         splits = int(min(n_tiles, max(1, round(c * n_tiles / target))))
         for s in range(splits):
@@ -503,6 +510,8 @@ def schedule_wgrad(units: List[WgradUnit], n_tiles: int, n_workers: int):
                 items.append((c * (t1 - t0), NbWgradItem(tile_begin=t0, tile_end=t1, n_dy_slabs=u.n_dy_slabs,
                                                          n_x_slabs=u.n_x_slabs, dy_slab=u.dy_slab, x_slab=u.x_slab,
                                                          m_real=u.m_real, n_real=u.n_real, dst=u.dst, ld=u.ld,
-                                                         bias_dst=u.bias_dst, mode=u.mode, coef_dst=u.coef_dst)))
+                                                         bias_dst=u.bias_dst, mode=u.mode, coef_dst=u.coef_dst,
+                                                         z_slab=u.z_slab, n_z_slabs=u.n_z_slabs, z_first=u.z_first,
+                                                         zbias_dst=u.zbias_dst)))
     items.sort(key=lambda t: -t[0])
     return [it for _, it in items]

@@ -41,6 +41,9 @@ for name, f in fields.items():
         byt = {"garf_fwd_train": y + z, "garf_bwd": z + dy, "garf_wgrad": y + dy + z}[k]
         out[f"{name}.{k}"] = {"ms": round(ms, 4), "tflops": round(flops / ms / 1e9, 1), "stash_GBps": round(byt / ms / 1e6, 1),
                               "stash_MB": round(byt / 1e6, 1)}
+        if k == "garf_wgrad":     # what the kernel actually streams: every unit's dY + X + Z slabs (dY slabs are re-read per X block)
+            rd = sum(u.n_dy_slabs + u.n_x_slabs + u.n_z_slabs for u in cg.units) * 16384 * n_tiles
+            out[f"{name}.{k}"].update(read_MB=round(rd / 1e6, 1), read_GBps=round(rd / ms / 1e6, 1))
     f.timers = None
 eng.capture(o, d, tgt)
 for _ in range(3):

@@ -187,13 +187,15 @@ def weight_gradients(units, params, grad, y_stash, dy_stash, z_stash):
     """Accumulates one tile's contribution of every weight-gradient unit into `grad` (flat fp32)."""
     for u in units:
         dyv = th.cat([dy_stash[u.dy_slab + j] for j in range(u.n_dy_slabs)], dim=1)[:, :u.m_real]
-        if u.mode == _lib.WGRAD_COLSUM:
-            zv = th.cat([z_stash[u.x_slab + j] for j in range(u.n_x_slabs)], dim=1)[:, :u.m_real]
-            if u.bias_dst >= 0:
-                grad[u.bias_dst: u.bias_dst + u.m_real] += dyv.sum(0)
+        if u.n_z_slabs > 0:      # z duty: bias and Gaussian-width gradients of dY slabs z_first .. z_first + n_z - 1
+            c0, c1 = 64 * u.z_first, min(64 * (u.z_first + u.n_z_slabs), u.m_real)
+            zv = th.cat([z_stash[u.z_slab + j] for j in range(u.n_z_slabs)], dim=1)[:, :c1 - c0]
+            if u.zbias_dst >= 0:
+                grad[u.zbias_dst + c0: u.zbias_dst + c1] += dyv[:, c0:c1].sum(0)
             if u.coef_dst >= 0:
-                s = params[u.coef_dst: u.coef_dst + u.m_real]
-                grad[u.coef_dst: u.coef_dst + u.m_real] += (zv * dyv).sum(0) * s / (s * s + 1e-6)
+                s = params[u.coef_dst + c0: u.coef_dst + c1]
+                grad[u.coef_dst + c0: u.coef_dst + c1] += (zv * dyv[:, c0:c1]).sum(0) * s / (s * s + 1e-6)
+        if u.mode == _lib.WGRAD_COLSUM:
             continue
         xv = th.cat([y_stash[u.x_slab + j] for j in range(u.n_x_slabs)], dim=1)[:, :u.n_real]
         dw = dyv.T @ xv                                                       # (m_real, n_real)
