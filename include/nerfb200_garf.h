@@ -98,7 +98,10 @@ typedef struct {
   int8_t n_chunks;          /* 0: no MMA (the op only marks a point in the completion order)    */
   int8_t n_blocks;          /* 1 or 2 N-blocks per K step                                       */
   int8_t accumulate;        /* 1: the first MMA adds to what the accumulator columns hold       */
-  int8_t reserved;
+  int8_t early;             /* 1: step k is a Gaussian step that publishes its slabs one by one   */
+                            /* (slab_ready barriers) and op k writes none of the accumulator     */
+                            /* columns step k reads: chunk c is issued as soon as ITS slab is     */
+                            /* published, i.e. the MMAs of op k run under the epilogue of step k  */
   int8_t a_slab[NG_MAX_CHUNKS];
   int8_t k16[NG_MAX_CHUNKS];     /* 16-wide K steps of every chunk (1..4)                        */
   int16_t w_rows;                /* rows of every weight image of this op (<= 256)               */

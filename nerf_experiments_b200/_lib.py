@@ -133,7 +133,7 @@ class NgBlock(C.Structure):
 
 
 class NgOp(C.Structure):
-    _fields_ = [("n_chunks", C.c_int8), ("n_blocks", C.c_int8), ("accumulate", C.c_int8), ("reserved", C.c_int8),
+    _fields_ = [("n_chunks", C.c_int8), ("n_blocks", C.c_int8), ("accumulate", C.c_int8), ("early", C.c_int8),
                 ("a_slab", C.c_int8 * NG_MAX_CHUNKS), ("k16", C.c_int8 * NG_MAX_CHUNKS), ("w_rows", C.c_int16),
                 ("reserved2", C.c_int16), ("w_off", C.c_int32 * NG_MAX_CHUNKS), ("blocks", NgBlock * 2)]
 

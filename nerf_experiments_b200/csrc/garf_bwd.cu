@@ -163,6 +163,7 @@ garf_bwd_kernel(const __grid_constant__ GarfBwdParams p) {
           const int ncols = 64 * nsl;
           const float4* coef4 = reinterpret_cast<const float4*>(sm.floats + st.coef_off + 16 * cq);
           const bool direct = (flags & NG_F_DIRECT) != 0;
+          const bool early_step = k < n_ops && sm.ops[k].early != 0;
           const bool first = (flags & NG_F_FIRST_LAYER) != 0;
           const bool grads = want && (st.skip_src != 0);
           const bool add_hold = (flags & NG_F_HOLD_ADD) != 0;
@@ -215,6 +216,7 @@ garf_bwd_kernel(const __grid_constant__ GarfBwdParams p) {
               const uint32_t sb = slab_base + (uint32_t)(st.out_slab + j) * NB_SLAB_BYTES;
               sts128g(sb + off0, dp[0], dp[1], dp[2], dp[3]);
               sts128g(sb + off1, dp[4], dp[5], dp[6], dp[7]);
+              if (early_step) publish_slab(sm, st.out_slab + j, lane);   // the op's chunk on this slab may go
             }
           };
           tmem_ld16(acc_q, va);
@@ -235,7 +237,7 @@ garf_bwd_kernel(const __grid_constant__ GarfBwdParams p) {
             if (st.skip_src == 2) { ddir[0] += acc3[0]; ddir[1] += acc3[1]; ddir[2] += acc3[2]; }
             else { dpos[0] += acc3[0]; dpos[1] += acc3[1]; dpos[2] += acc3[2]; }
           }
-          if (k < n_ops) publish_step(sm, g, !direct, lane);
+          if (k < n_ops) publish_step(sm, g, !direct && !early_step, lane);
         } else if (kind == NG_BSTEP_PLAIN) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {

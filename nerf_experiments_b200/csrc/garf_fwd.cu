@@ -154,6 +154,7 @@ garf_fwd_kernel(const __grid_constant__ GarfFwdParams p) {
           const float sx = st.skip_src == 2 ? md.x : mp.x, sy = st.skip_src == 2 ? md.y : mp.y,
                       sz = st.skip_src == 2 ? md.z : mp.z;
           const uint32_t acc_q = tmem_lane + (uint32_t)(st.src_col + 16 * cq);
+          const bool early_step = k < n_ops && sm.ops[k].early != 0;
           uint32_t zp[4][8];
           uint32_t va[16], vb[16];
           // one 16-column group: bias (+ rank-3 fp32 skip), Gaussian, bf16 packs of y (-> slab) and z (-> stash)
@@ -183,6 +184,7 @@ garf_fwd_kernel(const __grid_constant__ GarfFwdParams p) {
             const uint32_t sb = slab_base + (uint32_t)(st.out_slab + j) * NB_SLAB_BYTES;
             sts128g(sb + off0, yp[0], yp[1], yp[2], yp[3]);
             sts128g(sb + off1, yp[4], yp[5], yp[6], yp[7]);
+            if (early_step) publish_slab(sm, st.out_slab + j, lane);   // the op's chunk on this slab may go
           };
           // the TMEM load of group j + 1 is in flight during the math of group j
           tmem_ld16(acc_q, va);
@@ -199,7 +201,7 @@ garf_fwd_kernel(const __grid_constant__ GarfFwdParams p) {
               group(vb, j + 1);
             }
           }
-          publish_step(sm, g, true, lane);
+          publish_step(sm, g, !early_step, lane);
 #ifndef NG_EXP_NO_Z
           if (training && st.z_stash >= 0) {
 #else

@@ -10,9 +10,18 @@
 //   acc_full[g & 1]  MMA warp (tcgen05.commit) -> row warps: op g and every op before it completed
 //   drained[g & 1]   stash warp -> row warps: the HBM copies of the slabs published by step g have
 //                    read shared memory
+//   slab_ready[s]    16 row warps -> MMA warp, stash warp, only in steps whose op is `early`
+//                    (NgOp.early: a Gaussian step that publishes slabs, followed by an op that writes
+//                    none of the accumulator columns the step reads): slab s of the step is written.
+//                    Chunk c of the op is issued as soon as ITS slab is there, so the MMAs of op k run
+//                    under the epilogue of step k; in_ready[g & 1] of such a step is still arrived at
+//                    (and consumed by both roles) when the whole step is done. The row warps do not
+//                    fence these publications: the consumer executes the generic -> async proxy fence
+//                    after it has acquired the barrier phase (tc.cuh, consumer_proxy_fence).
 // A waiter never falls two phases behind a barrier: step k consumes the completions of every op up
 // to k - 1 - wait_lag (wait_lag <= 1) before it does anything, and op k + 1 cannot be issued before
-// step k + 1 has arrived.
+// step k + 1 has arrived; the MMA warp and the stash warp consume every slab_ready completion of an
+// early step before they leave that step.
 #pragma once
 #include "common.cuh"
 #include "garf.h"
@@ -50,6 +59,7 @@ struct GarfSmem {
   uint64_t* in_ready;   // [2]
   uint64_t* acc_full;   // [2]
   uint64_t* drained;    // [2]
+  uint64_t* slab_ready; // [NG_N_SLABS]
   uint32_t* tmem_ptr;
   float4* pos;          // [128] query position of every tile row
   float4* dir;          // [128] ray direction of every tile row
@@ -66,7 +76,8 @@ struct GarfSmem {
     in_ready = empty + NG_N_STAGES;
     acc_full = in_ready + 2;
     drained = acc_full + 2;
-    tmem_ptr = reinterpret_cast<uint32_t*>(drained + 2);
+    slab_ready = drained + 2;
+    tmem_ptr = reinterpret_cast<uint32_t*>(slab_ready + NG_N_SLABS);
     pos = reinterpret_cast<float4*>(c + kCtrlBytes);
     dir = pos + NB_TILE_ROWS;
     floats = reinterpret_cast<float*>(c + kCtrlBytes + kXyzBytes);
@@ -95,11 +106,12 @@ struct GarfSmem {
       mbar_init(&acc_full[b], 1);
       mbar_init(&drained[b], 1);
     }
+    for (int i = 0; i < NG_N_SLABS; ++i) mbar_init(&slab_ready[i], kRowWarpsG);
     fence_barrier_init();
   }
 };
 static_assert(GarfSmem::bytes() <= 227 * 1024, "shared memory budget of the GARF kernels");
-static_assert((2 * NG_N_STAGES + 6) * 8 + 4 <= GarfSmem::kCtrlBytes, "control block layout");
+static_assert((2 * NG_N_STAGES + 6 + NG_N_SLABS) * 8 + 4 <= GarfSmem::kCtrlBytes, "control block layout");
 
 // phase parity of the g-th use of a pair of alternating barriers
 __device__ __forceinline__ uint32_t pair_parity(uint32_t g) { return (g >> 1) & 1u; }
@@ -129,6 +141,12 @@ __device__ __forceinline__ void publish_step(const GarfSmem& sm, uint32_t g, boo
   tcgen05_fence_before();
   __syncwarp();
   if (lane == 0) mbar_arrive(&sm.in_ready[g & 1u]);
+}
+
+// early steps: one slab of the step is written (no proxy fence here: the consumers fence)
+__device__ __forceinline__ void publish_slab(const GarfSmem& sm, int slab, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&sm.slab_ready[slab]);
 }
 
 // ---- weight producer (one thread) -------------------------------------------------------------
@@ -162,10 +180,14 @@ __device__ __forceinline__ void mma_loop(const NgProgram& prog, const GarfSmem& 
   const uint32_t ring0 = smem_u32(sm.ring(0)) >> 4;
   const bool elected = elect_one();
   uint32_t stage = 0, phase = 0, g = 0;
+  uint32_t slab_par = 0;     // phase parity of every slab_ready barrier (early steps)
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     for (int k = 0; k < prog.n_ops; ++k, ++g) {
       const NgOp& op = sm.ops[k];
       const int n_chunks = op.n_chunks, n_blocks = op.n_blocks;
+      const bool early = op.early != 0;
+      // slabs step k publishes one by one (early ops only)
+      uint32_t pending = early ? (((1u << sm.steps[k].n_slabs) - 1u) << sm.steps[k].out_slab) : 0u;
       uint32_t idesc[2], tcol[2], brow[2];
 #pragma unroll
       for (int b = 0; b < 2; ++b) {
@@ -175,13 +197,22 @@ __device__ __forceinline__ void mma_loop(const NgProgram& prog, const GarfSmem& 
         brow[b] = (uint32_t)blk.row0 * 8u;               // row0 * 128 B >> 4
       }
       uint32_t acc = op.accumulate ? 1u : 0u;
-      mbar_wait(&sm.in_ready[g & 1u], pair_parity(g));
-      consumer_proxy_fence();
-      tcgen05_fence_after();
+      if (!early) {
+        mbar_wait(&sm.in_ready[g & 1u], pair_parity(g));
+        consumer_proxy_fence();
+        tcgen05_fence_after();
+      }
       for (int c = 0; c < n_chunks; ++c) {
         const uint32_t a_lo = slab0 + (uint32_t)op.a_slab[c] * (NB_SLAB_BYTES >> 4);
         const uint32_t b_lo = ring0 + stage * (NB_RING_STAGE_BYTES >> 4);
         const int k16 = op.k16[c];
+        if ((pending >> op.a_slab[c]) & 1u) {      // this chunk's slab is being written by step k
+          const uint32_t s = (uint32_t)op.a_slab[c];
+          mbar_wait(&sm.slab_ready[s], (slab_par >> s) & 1u);
+          slab_par ^= 1u << s;
+          pending &= ~(1u << s);
+          fence_proxy_async();
+        }
         mbar_wait(&sm.full[stage], phase);
         tcgen05_fence_after();
 #pragma unroll
@@ -201,6 +232,16 @@ __device__ __forceinline__ void mma_loop(const NgProgram& prog, const GarfSmem& 
         if (elected) umma_commit(&sm.empty[stage]);
         if (++stage == (uint32_t)NG_N_STAGES) { stage = 0; phase ^= 1u; }
       }
+      if (early) {   // consume what is left of step k: slabs no chunk read, and the step's own completion
+        while (pending) {
+          const uint32_t s = (uint32_t)__ffs(pending) - 1u;
+          mbar_wait(&sm.slab_ready[s], (slab_par >> s) & 1u);
+          slab_par ^= 1u << s;
+          pending &= pending - 1u;
+        }
+        mbar_wait(&sm.in_ready[g & 1u], pair_parity(g));
+        tcgen05_fence_after();
+      }
       if (elected) umma_commit(&sm.acc_full[g & 1u]);
       __syncwarp();
     }
@@ -210,11 +251,29 @@ __device__ __forceinline__ void mma_loop(const NgProgram& prog, const GarfSmem& 
 // ---- stash copier (one thread): slabs published by step k -> the per-tile HBM stash ------------
 __device__ __forceinline__ void stash_copier_loop(const NgProgram& prog, const GarfSmem& sm, int n_tiles,
                                                   uint8_t* stash, int slabs_per_tile) {
-  uint32_t g = 0;
+  uint32_t g = 0, slab_par = 0;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     uint8_t* tile_stash = stash + (size_t)tile * (size_t)slabs_per_tile * NB_SLAB_BYTES;
     for (int k = 0; k < prog.n_ops; ++k, ++g) {
       const NgStep& st = sm.steps[k];
+      if (sm.ops[k].early) {
+        // the slabs of an early step arrive one by one: every copy leaves as soon as its slab is written
+        for (int j = 0; j < st.n_slabs; ++j) {
+          const uint32_t s = (uint32_t)(st.out_slab + j);
+          mbar_wait(&sm.slab_ready[s], (slab_par >> s) & 1u);
+          slab_par ^= 1u << s;
+          fence_proxy_async();
+#ifndef NG_EXP_NO_Y
+          if (st.y_stash >= 0)
+            bulk_s2g(tile_stash + (size_t)(st.y_stash + j) * NB_SLAB_BYTES, sm.slab(st.out_slab + j), NB_SLAB_BYTES);
+#endif
+        }
+        mbar_wait(&sm.in_ready[g & 1u], pair_parity(g));
+        bulk_commit();
+        bulk_wait_read<0>();
+        mbar_arrive(&sm.drained[g & 1u]);
+        continue;
+      }
       mbar_wait(&sm.in_ready[g & 1u], pair_parity(g));
       consumer_proxy_fence();
       if (st.y_stash >= 0 && st.out_slab >= 0 && !(st.flags & NG_F_DIRECT)) {

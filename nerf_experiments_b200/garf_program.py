@@ -109,6 +109,22 @@ class _Builder:
             o.blocks[b] = NgBlock(tmem_col=col, n=n, row0=row0, reserved=0)
         self.ops.append(o)
 
+    @staticmethod
+    def _early_ok(st, o) -> bool:
+        """May the MMAs of op k start slab by slab while step k is still running (include/nerfb200_garf.h,
+        NgOp.early)? Only behind a Gaussian step that publishes slabs, and only if the op writes no accumulator
+        column that step still has to read."""
+        if o.n_chunks == 0 or st.out_slab < 0 or st.n_slabs <= 0 or (st.flags & NG_F_DIRECT):
+            return False
+        if st.kind not in (NG_STEP_ACT, NG_BSTEP_ACT):
+            return False
+        lo, hi = st.src_col, st.src_col + 64 * st.n_slabs
+        for b in range(o.n_blocks):
+            c0, c1 = o.blocks[b].tmem_col, o.blocks[b].tmem_col + o.blocks[b].n
+            if c0 < hi and lo < c1:
+                return False
+        return True
+
     def nop(self):
         self.ops.append(NgOp())
 
@@ -122,6 +138,7 @@ class _Builder:
         prog.n_ops = len(self.ops)
         prog.n_floats = self.n_floats
         for i, o in enumerate(self.ops):
+            o.early = int(self._early_ok(self.steps[i], o))
             prog.ops[i] = o
         for i, s in enumerate(self.steps):
             prog.steps[i] = s
@@ -278,8 +295,8 @@ def compile_radiance(L: List[GaussLinear], Lc: List[GaussLinear]) -> CompiledGar
     _act_layer_fwd(f, L2, R1, 0, y2, z2)
     _mma_fwd(f, L3.lin, [0, 1, 2, 3], 0, 0, 128, R0)
     _act_layer_fwd(f, L3, R0, 0, y3, z3)
-    _mma_fwd(f, L4.lin, [0, 1], 0, 0, 128, R0)
-    _act_layer_fwd(f, L4, R0, HOLD, y4, z4)                               # z1 stays in the hold slabs
+    _mma_fwd(f, L4.lin, [0, 1], 0, 0, 128, R1)      # regions alternate: an op never overwrites the columns the step in front of it reads,
+    _act_layer_fwd(f, L4, R1, HOLD, y4, z4)         # so its MMAs may start slab by slab (NgOp.early); z1 stays in the hold slabs
     for blk in range(2):                     # 131 -> 512 in two column blocks, 512 -> 256 accumulating in R1
         if blk > 0:
             f.step(NG_STEP_NONE, lag=1)
@@ -289,14 +306,14 @@ def compile_radiance(L: List[GaussLinear], Lc: List[GaussLinear]) -> CompiledGar
     _act_layer_fwd(f, L6, R1, 0, y6, z6)
     _mma_fwd(f, L7.lin, [0, 1, 2, 3], 0, 0, 128, R0)
     _act_layer_fwd(f, L7, R0, 0, y7, z7)
-    _mma_fwd(f, L8.lin, [0, 1], 0, 0, 128, R0, extra_row=(128, 128))      # density = column 128 (garf/model_radiance.py:91)
+    _mma_fwd(f, L8.lin, [0, 1], 0, 0, 128, R1, extra_row=(128, R1 + 128))  # density = column 128 (garf/model_radiance.py:91)
     bias8 = f.pack(L8.lin.b_off, 129, 144)
-    f.step(NG_STEP_LINEAR, n_slabs=2, out_slab=0, src_col=R0, bias_off=bias8, res_slab=HOLD, flags=NG_F_SIGMA,
-           sigma_col=128, y_stash=ysum)                                   # z1 + z2[:, :128]  (:93)
+    f.step(NG_STEP_LINEAR, n_slabs=2, out_slab=0, src_col=R1, bias_off=bias8, res_slab=HOLD, flags=NG_F_SIGMA,
+           sigma_col=R1 + 128, y_stash=ysum)                              # z1 + z2[:, :128]  (:93)
     _mma_fwd(f, C1.lin, [0, 1], 0, 0, 256, R0)
     _act_layer_fwd(f, C1, R0, 0, yc1, zc1, skip=(2, 128))
-    _mma_fwd(f, C2.lin, [0, 1, 2, 3], 0, 0, 3, R0)
-    f.step(NG_STEP_RGB, src_col=R0, bias_off=f.pack(C2.lin.b_off, 3, 16))
+    _mma_fwd(f, C2.lin, [0, 1, 2, 3], 0, 0, 3, R1)
+    f.step(NG_STEP_RGB, src_col=R1, bias_off=f.pack(C2.lin.b_off, 3, 16))
     fwd = NgProgram()
     f.finish(fwd)
     fwd.y_slabs_per_tile, fwd.z_slabs_per_tile = ys.n, zs.n
@@ -318,12 +335,12 @@ def compile_radiance(L: List[GaussLinear], Lc: List[GaussLinear]) -> CompiledGar
     _mma_bwd(g, C2.lin, [0], [(0, 3)], 0, 256, R0)
     g.step(NG_BSTEP_ACT, n_slabs=4, out_slab=0, src_col=R0, coef_off=coef(C1, 0, 256), z_stash=zc1, y_stash=d_c1,
            skip_src=2, skip_off=g.pack_skip(C1.lin, 0, 256, 128))
-    _mma_bwd(g, C1.lin, [0, 1, 2, 3], [(64 * c, 64) for c in range(4)], 0, 128, R0)
-    g.step(NG_BSTEP_PLAIN, n_slabs=2, out_slab=0, src_col=R0, flags=NG_F_HOLD_SAVE | NG_F_SIGMA, y_stash=d_8)
+    _mma_bwd(g, C1.lin, [0, 1, 2, 3], [(64 * c, 64) for c in range(4)], 0, 128, R1)
+    g.step(NG_BSTEP_PLAIN, n_slabs=2, out_slab=0, src_col=R1, flags=NG_F_HOLD_SAVE | NG_F_SIGMA, y_stash=d_8)
     _mma_bwd(g, L8.lin, [0, 1, 2], [(0, 64), (64, 64), (128, 1)], 0, 128, R0)
     g.step(NG_BSTEP_ACT, n_slabs=2, out_slab=0, src_col=R0, coef_off=coef(L7, 0, 128), z_stash=z7, y_stash=d_7)
-    _mma_bwd(g, L7.lin, [0, 1], [(0, 64), (64, 64)], 0, 256, R0)
-    g.step(NG_BSTEP_ACT, n_slabs=4, out_slab=0, src_col=R0, coef_off=coef(L6, 0, 256), z_stash=z6, y_stash=d_6)
+    _mma_bwd(g, L7.lin, [0, 1], [(0, 64), (64, 64)], 0, 256, R1)
+    g.step(NG_BSTEP_ACT, n_slabs=4, out_slab=0, src_col=R1, coef_off=coef(L6, 0, 256), z_stash=z6, y_stash=d_6)
     for blk in range(4):        # d(y5) in four 128-column blocks (R0), d(z1) accumulating in R1
         if blk > 0:
             g.step(NG_STEP_NONE, lag=1)
@@ -335,8 +352,8 @@ def compile_radiance(L: List[GaussLinear], Lc: List[GaussLinear]) -> CompiledGar
            flags=NG_F_HOLD_ADD)                                           # + the residual path (z1 + z2)
     _mma_bwd(g, L4.lin, [0, 1], [(0, 64), (64, 64)], 0, 128, R0)
     g.step(NG_BSTEP_ACT, n_slabs=2, out_slab=0, src_col=R0, coef_off=coef(L3, 0, 128), z_stash=z3, y_stash=d_3)
-    _mma_bwd(g, L3.lin, [0, 1], [(0, 64), (64, 64)], 0, 256, R0)
-    g.step(NG_BSTEP_ACT, n_slabs=4, out_slab=0, src_col=R0, coef_off=coef(L2, 0, 256), z_stash=z2, y_stash=d_2)
+    _mma_bwd(g, L3.lin, [0, 1], [(0, 64), (64, 64)], 0, 256, R1)
+    g.step(NG_BSTEP_ACT, n_slabs=4, out_slab=0, src_col=R1, coef_off=coef(L2, 0, 256), z_stash=z2, y_stash=d_2)
     _first_layer_bwd(g, L1, L2, z1, d_1)
     bwd = NgProgram()
     g.finish(bwd)
@@ -414,8 +431,8 @@ def compile_proposal(L: List[GaussLinear]) -> CompiledGarf:
     _act_layer_fwd(f, L2, R1, 0, y2, z2)
     _mma_fwd(f, L3.lin, [0, 1, 2, 3], 0, 0, 128, R0)
     _act_layer_fwd(f, L3, R0, 0, y3, z3)
-    _mma_fwd(f, L4.lin, [0, 1], 0, 0, 1, R0)
-    f.step(NG_STEP_SIGMA, src_col=R0, bias_off=f.pack(L4.lin.b_off, 1, 16))
+    _mma_fwd(f, L4.lin, [0, 1], 0, 0, 1, R1)
+    f.step(NG_STEP_SIGMA, src_col=R1, bias_off=f.pack(L4.lin.b_off, 1, 16))
     fwd = NgProgram()
     f.finish(fwd)
     fwd.y_slabs_per_tile, fwd.z_slabs_per_tile = ys.n, zs.n
@@ -431,8 +448,8 @@ def compile_proposal(L: List[GaussLinear]) -> CompiledGarf:
     g.step(NG_BSTEP_HEAD, n_slabs=1, out_slab=0, flags=NG_F_SIGMA, y_stash=d_head)
     _mma_bwd(g, L4.lin, [0], [(0, 1)], 0, 128, R0)
     g.step(NG_BSTEP_ACT, n_slabs=2, out_slab=0, src_col=R0, coef_off=coef(L3, 0, 128), z_stash=z3, y_stash=d_3)
-    _mma_bwd(g, L3.lin, [0, 1], [(0, 64), (64, 64)], 0, 256, R0)
-    g.step(NG_BSTEP_ACT, n_slabs=4, out_slab=0, src_col=R0, coef_off=coef(L2, 0, 256), z_stash=z2, y_stash=d_2)
+    _mma_bwd(g, L3.lin, [0, 1], [(0, 64), (64, 64)], 0, 256, R1)
+    g.step(NG_BSTEP_ACT, n_slabs=4, out_slab=0, src_col=R1, coef_off=coef(L2, 0, 256), z_stash=z2, y_stash=d_2)
     _first_layer_bwd(g, L1, L2, z1, d_1)
     bwd = NgProgram()
     g.finish(bwd)
