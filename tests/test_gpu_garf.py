@@ -195,10 +195,12 @@ def test_garf_model_chain_matches_oracle(cuda, training):
     u = (th.rand(B, generator=gen), th.rand(B, generator=gen)) if training else None
     sd_p = {k: v.detach().cpu().clone().requires_grad_() for k, v in m.proposal_network.state_dict().items()}
     sd_r = {k: v.detach().cpu().clone().requires_grad_() for k, v in m.radiance_network.state_dict().items()}
+    o_r, d_r = o.clone().requires_grad_(), d.clone().requires_grad_()      # the pose refinement's path: d(loss) / d(rays)
     r_rgb, r_op, r_dp, r_lp, (r0, r1) = ref_garf.garf_forward(
-        sd_p, sd_r, o, d, 2.0, 7.0, 32, 48, None if u is None else u[0], None if u is None else u[1])
+        sd_p, sd_r, o_r, d_r, 2.0, 7.0, 32, 48, None if u is None else u[0], None if u is None else u[1])
     uc = None if u is None else (u[0].to(cuda), u[1].to(cuda))
-    rgb, (lp, lr) = m._forward_loss((o.to(cuda), d.to(cuda), target.to(cuda)), uc)
+    o_c, d_c = o.to(cuda).requires_grad_(), d.to(cuda).requires_grad_()
+    rgb, (lp, lr) = m._forward_loss((o_c, d_c, target.to(cuda)), uc)
     _, opacity, depth, extras = m(o.to(cuda), d.to(cuda), uc)
     # The oracle runs the networks in fp32, the fused kernels with bf16 operands: the proposal densities
     # differ by ~1 %, so the resampled intervals (a continuous function of the proposal cdf) move by a
@@ -216,6 +218,9 @@ def test_garf_model_chain_matches_oracle(cuda, training):
         assert _rel(p.grad.cpu(), sd_r[n].grad) < 0.25, n               # bf16 operands vs fp32 (as the ReLU network)
     for n, p in m.proposal_network.named_parameters():
         assert _rel(p.grad.cpu(), sd_p[n].grad) < 0.35, n
+    # ray gradients (radiance and proposal-loss paths together; sampling is not differentiated on either side)
+    assert _rel(o_c.grad.cpu(), o_r.grad) < 0.3, _rel(o_c.grad.cpu(), o_r.grad)
+    assert _rel(d_c.grad.cpu(), d_r.grad) < 0.3, _rel(d_c.grad.cpu(), d_r.grad)
 
 
 @pytest.mark.parametrize("B,S", [(1, 1), (7, 33), (64, 64), (300, 192)])
