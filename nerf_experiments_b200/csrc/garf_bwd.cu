@@ -173,8 +173,9 @@ garf_bwd_kernel(const __grid_constant__ GarfBwdParams p) {
           uint32_t va[16], vb[16];
           auto group = [&](const uint32_t (&v)[16], int j) {
             uint32_t dp[8];
-            uint32_t zz[8];
-            unswap_row(zq[j & 1], odd_row, zz);
+            uint32_t zz[8];      // the z stash keeps a thread's 16 columns in natural order (garf_kernels.cuh)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) zz[i] = zq[j & 1].w[i];
             if (j + 2 < nsl)       // the slot is free again: request the group after the next
               zq[j & 1] = ldg256_stream(zbase + (size_t)(j + 2) * NB_SLAB_BYTES + sec_off);
 #pragma unroll

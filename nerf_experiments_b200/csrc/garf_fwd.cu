@@ -143,7 +143,7 @@ garf_fwd_kernel(const __grid_constant__ GarfFwdParams p) {
             uint8_t* zs = ztile + (size_t)(st.z_stash + sib) * NB_SLAB_BYTES;
 #pragma unroll
             for (int r = 0; r < 16; ++r)
-              *reinterpret_cast<uint32_t*>(zs + slab_offset((uint32_t)(rg * 16 + r), (uint32_t)(2 * lane))) = zp[r];
+              *reinterpret_cast<uint32_t*>(zs + zstash_offset((uint32_t)(rg * 16 + r), (uint32_t)(2 * lane))) = zp[r];
           }
         } else if (kind == NG_STEP_ACT) {
           const int ncols = 64 * nsl;
@@ -155,11 +155,15 @@ garf_fwd_kernel(const __grid_constant__ GarfFwdParams p) {
                       sz = st.skip_src == 2 ? md.z : mp.z;
           const uint32_t acc_q = tmem_lane + (uint32_t)(st.src_col + 16 * cq);
           const bool early_step = k < n_ops && sm.ops[k].early != 0;
-          uint32_t zp[4][8];
+#ifndef NG_EXP_NO_Z
+          const bool z_now = training && st.z_stash >= 0;
+#else
+          const bool z_now = false;
+#endif
           uint32_t va[16], vb[16];
           // one 16-column group: bias (+ rank-3 fp32 skip), Gaussian, bf16 packs of y (-> slab) and z (-> stash)
           auto group = [&](const uint32_t (&v)[16], int j) {
-            uint32_t yp[8];
+            uint32_t yp[8], zp[8];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const float4 b = bias4[16 * j + q], c = coef4[16 * j + q];
@@ -178,13 +182,18 @@ garf_fwd_kernel(const __grid_constant__ GarfFwdParams p) {
               const float y2 = ex2f(z2 * z2 * c.z), y3 = ex2f(z3 * z3 * c.w);
               yp[2 * q] = pack_bf16(y0, y1);
               yp[2 * q + 1] = pack_bf16(y2, y3);
-              zp[j][2 * q] = pack_bf16(z0, z1);
-              zp[j][2 * q + 1] = pack_bf16(z2, z3);
+              zp[2 * q] = pack_bf16(z0, z1);
+              zp[2 * q + 1] = pack_bf16(z2, z3);
             }
             const uint32_t sb = slab_base + (uint32_t)(st.out_slab + j) * NB_SLAB_BYTES;
             sts128g(sb + off0, yp[0], yp[1], yp[2], yp[3]);
             sts128g(sb + off1, yp[4], yp[5], yp[6], yp[7]);
             if (early_step) publish_slab(sm, st.out_slab + j, lane);   // the op's chunk on this slab may go
+            // Early steps publish without a proxy fence in the row warps (the consumers fence), so the z stores
+            // leave right away instead of sitting in 32 registers until the step is published. (Behind a step
+            // that is not early, the writer-side fence of publish_step would wait for their acknowledgement:
+            // slower, still correct — every Gaussian step of the two GARF programs is early.)
+            if (z_now) stg256(ztile + (size_t)(st.z_stash + j) * NB_SLAB_BYTES + sec_off, zp);
           };
           // the TMEM load of group j + 1 is in flight during the math of group j
           tmem_ld16(acc_q, va);
@@ -202,20 +211,6 @@ garf_fwd_kernel(const __grid_constant__ GarfFwdParams p) {
             }
           }
           publish_step(sm, g, !early_step, lane);
-#ifndef NG_EXP_NO_Z
-          if (training && st.z_stash >= 0) {
-#else
-          if (false) {
-#endif
-            // after the publication: a global store in flight would make the proxy fence wait for its ack
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (j < nsl) {
-                uint8_t* zs = ztile + (size_t)(st.z_stash + j) * NB_SLAB_BYTES;
-                stg256_row(zs + sec_off, odd_row, zp[j]);
-              }
-            }
-          }
         } else if (kind == NG_STEP_LINEAR) {
           const float* bias = sm.floats + st.bias_off + 16 * cq;
 #pragma unroll

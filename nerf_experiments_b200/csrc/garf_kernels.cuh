@@ -354,6 +354,18 @@ __device__ __forceinline__ void stg256_row(void* sec, bool odd, const uint32_t (
                "r"(odd ? v[0] : v[4]), "r"(odd ? v[1] : v[5]), "r"(odd ? v[2] : v[6]), "r"(odd ? v[3] : v[7])
                : "memory");
 }
+__device__ __forceinline__ void stg256(void* sec, const uint32_t (&v)[8]) {
+  asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(sec),
+               "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+// Z stash layout (private to garf_fwd, garf_bwd and the column sums of mlp_wgrad; never an MMA operand): the
+// slab layout with the two 16-byte halves of every 32-byte sector in NATURAL order on all rows, so the row
+// thread that owns the sector stores / loads its 16 columns as they are (the slab layout proper swaps
+// the halves on odd rows: eight SELs per access). Byte offset of element (row, col) inside a z slab:
+__host__ __device__ __forceinline__ uint32_t zstash_offset(uint32_t row, uint32_t col) {
+  return row * 128u + ((((col >> 4) ^ ((row & 7u) >> 1)) & 3u) << 5) + ((col & 15u) << 1);
+}
 // raw sector (halves in memory order); `unswap_row` restores the logical order
 struct Sector32 { uint32_t w[8]; };
 __device__ __forceinline__ Sector32 ldg256_stream(const void* sec) {

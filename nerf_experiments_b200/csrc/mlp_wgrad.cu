@@ -176,7 +176,8 @@ mlp_wgrad_kernel(const __grid_constant__ WgradParams p) {
           if (sums) {
             const uint32_t lane_off = (uint32_t)(rg * 16) * 128u + (uint32_t)pc * 16u;
             const uint8_t* base = smem + stage * kStageBytes + (uint32_t)warp * kHalfSlabBytes + lane_off;
-            const uint8_t* zbase = smem + stage * kStageBytes + (zduty ? z_pos : 0u) * kHalfSlabBytes + lane_off;
+            const uint8_t* zslab = smem + stage * kStageBytes + (zduty ? z_pos : 0u) * kHalfSlabBytes + (uint32_t)(rg * 16) * 128u;
+            const uint8_t* zbase_x[2] = {zslab + (uint32_t)pc * 16u, zslab + (uint32_t)(pc ^ 1) * 16u};
 #pragma unroll
             for (int r8 = 0; r8 < 2; ++r8) {
 #pragma unroll
@@ -186,8 +187,9 @@ mlp_wgrad_kernel(const __grid_constant__ WgradParams p) {
                 bacc[q][2] += __uint_as_float(v.y << 16); bacc[q][3] += __uint_as_float(v.y & 0xffff0000u);
                 bacc[q][4] += __uint_as_float(v.z << 16); bacc[q][5] += __uint_as_float(v.z & 0xffff0000u);
                 bacc[q][6] += __uint_as_float(v.w << 16); bacc[q][7] += __uint_as_float(v.w & 0xffff0000u);
-                if (zduty) {   // Gaussian width gradient: sum over samples of z * dz (same position in the z slab)
-                  const uint4 z = *reinterpret_cast<const uint4*>(zbase + (uint32_t)(r8 * 8 + q) * 128u);
+                if (zduty) {   // Gaussian width gradient: sum over samples of z * dz. The z stash keeps the halves of a
+                               // 32-byte sector in natural order (garf_kernels.cuh): on odd rows the neighbouring chunk
+                  const uint4 z = *reinterpret_cast<const uint4*>(zbase_x[q & 1] + (uint32_t)(r8 * 8 + q) * 128u);
                   zacc[q][0] = fmaf(__uint_as_float(z.x << 16), __uint_as_float(v.x << 16), zacc[q][0]);
                   zacc[q][1] = fmaf(__uint_as_float(z.x & 0xffff0000u), __uint_as_float(v.x & 0xffff0000u), zacc[q][1]);
                   zacc[q][2] = fmaf(__uint_as_float(z.y << 16), __uint_as_float(v.y << 16), zacc[q][2]);
