@@ -59,12 +59,18 @@ garf_bwd_kernel(const __grid_constant__ GarfBwdParams p) {
   const uint32_t tmem_base = *sm.tmem_ptr;
 
   if (warp == kProducerWarpG) {
+    regs_helper();
     if (lane == 0) producer_loop(prog, p.wpack, sm, n_tiles);
   } else if (warp == kMmaWarpG) {
+    regs_helper();
     mma_loop(prog, sm, tmem_base, n_tiles);
   } else if (warp == kStashWarpG) {
+    regs_helper();
     if (lane == 0) stash_copier_loop(prog, sm, n_tiles, p.dy_stash, prog.y_slabs_per_tile);
+  } else if (warp >= kRowWarpsG) {
+    regs_helper();      // the idle warp of the helper warpgroup
   } else {
+    regs_row();
     const int row = threadIdx.x & 127;
     const int cq = threadIdx.x >> 7;
     const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);

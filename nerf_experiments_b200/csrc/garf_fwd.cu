@@ -51,12 +51,18 @@ garf_fwd_kernel(const __grid_constant__ GarfFwdParams p) {
   const uint32_t tmem_base = *sm.tmem_ptr;
 
   if (warp == kProducerWarpG) {
+    regs_helper();
     if (lane == 0) producer_loop(prog, p.wpack, sm, n_tiles);
   } else if (warp == kMmaWarpG) {
+    regs_helper();
     mma_loop(prog, sm, tmem_base, n_tiles);
   } else if (warp == kStashWarpG) {
+    regs_helper();
     if (training && lane == 0) stash_copier_loop(prog, sm, n_tiles, p.y_stash, prog.y_slabs_per_tile);
+  } else if (warp >= kRowWarpsG) {
+    regs_helper();      // the idle warp of the helper warpgroup
   } else {
+    regs_row();
     // ---------------- row threads ----------------
     const int row = threadIdx.x & 127;                  // tile row = TMEM lane
     const int cq = threadIdx.x >> 7;                    // 16-column quarter of every 64-column slab

@@ -39,7 +39,15 @@ constexpr int kRowThreadsG = 512;
 constexpr int kMmaWarpG = 16;
 constexpr int kProducerWarpG = 17;
 constexpr int kStashWarpG = 18;
-constexpr int kThreadsG = 608;
+// 20 warps: 16 row warps + MMA issuer, weight producer, stash copier and one idle warp that completes the
+// fifth warpgroup — setmaxnreg is a warpgroup-wide instruction. The kernels launch with 96 registers per
+// thread (640 x 96 = 60 K); the helper warpgroup then gives registers back (setmaxnreg.dec) and the four row
+// warpgroups take them (setmaxnreg.inc): the epilogues are the register-hungry part (spills at 96).
+constexpr int kThreadsG = 640;
+constexpr int kHelperRegsG = 56;
+constexpr int kRowRegsG = 104;
+__device__ __forceinline__ void regs_helper() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kHelperRegsG)); }
+__device__ __forceinline__ void regs_row() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRowRegsG)); }
 constexpr uint32_t kTmemColsG = 512;
 
 struct GarfSmem {
