@@ -44,10 +44,7 @@ constexpr int kStashWarpG = 18;
 // thread (640 x 96 = 60 K); the helper warpgroup then gives registers back (setmaxnreg.dec) and the four row
 // warpgroups take them (setmaxnreg.inc): the epilogues are the register-hungry part (spills at 96).
 constexpr int kThreadsG = 640;
-constexpr int kHelperRegsG = 56;
-constexpr int kRowRegsG = 104;
-__device__ __forceinline__ void regs_helper() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kHelperRegsG)); }
-__device__ __forceinline__ void regs_row() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRowRegsG)); }
+// (regs_helper / regs_row: mlp_kernels.cuh)
 constexpr uint32_t kTmemColsG = 512;
 
 struct GarfSmem {

@@ -22,6 +22,15 @@ constexpr int kMmaWarp = 16;
 constexpr int kProducerWarp = 17;
 constexpr int kStashWarp = 18;
 constexpr int kFwdThreads = 608;
+// Register rebalancing between warpgroups (setmaxnreg is a warpgroup-wide instruction; it must be executed
+// INSIDE the role's branch: ptxas budgets the code dominated by it). Used by the GARF kernels (640 threads =
+// 5 warpgroups at 96 registers: helper warpgroup 64, row warpgroups 104: their epilogues spill at 96). Tried on
+// mlp_fwd / mlp_bwd too and reverted: their row code fits 96 registers, while the MMA issuer loop of the ReLU
+// program spills at 64 (forward 1.05 -> 1.17 ms).
+constexpr int kHelperRegs = 64;      // 128 x 64 + 512 x 104 = 640 x 96
+constexpr int kRowRegs = 104;
+__device__ __forceinline__ void regs_helper() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kHelperRegs)); }
+__device__ __forceinline__ void regs_row() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRowRegs)); }
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kAccCols = 256;      // two accumulator buffers: consecutive ops alternate
 constexpr uint32_t kWeightCopyBytes = 8192;
