@@ -460,6 +460,14 @@ def run_extras(dev, peaks):
     ms_i = _timeit(lambda: ops.resample_icdf(edges, cdf, 192, u))
     bi = Br * (4 * 65 * 2 + 4 + 4 * 193)
     out["resample_icdf_64to192"] = {"ms": round(ms_i, 4), "GBps": round(bi / ms_i / 1e6, 1), "hbm_frac": round(bi / ms_i / 1e6 / hbm, 4)}
+    del tc0, tc1, w, edges, cdf, u
+    th.cuda.empty_cache()
+    try:       # the unmodified reference on the same GPU (checker-side; absent when oracle/_ref was not vendored)
+        ref_gpu = reference_on_gpu(dev, RAYS_PER_GPU)
+        if ref_gpu is not None:
+            out["c2_reference_modules_on_this_gpu"] = ref_gpu
+    except Exception as e:                                   # never let the optional line break the bench
+        out["c2_reference_modules_on_this_gpu"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
     return out
 
 
@@ -501,6 +509,50 @@ def cpu_baseline_sample(steps: int, rays: int, warmup: int = 1):
             "sample": f"{rays} rays x {SAMPLES} samples per step, best of {steps} after {warmup} warm-up: the unmodified "
                       f"reference BarfModel.training_step + backward (no optimizer step), fp32 torch CPU, oracle/_ref",
             "s_per_step": best}
+
+
+def reference_on_gpu(dev, rays: int, steps: int = 5, warmup: int = 2):
+    """SURVEY.md section 8(d), optional line: the UNMODIFIED reference modules (oracle/_ref) moved to the same
+    B200 — eager PyTorch with TF32 matmuls as barf/run_barf.py:101 sets them — timed on the bench workload's
+    step (BarfModel.training_step + backward + torch Adam, eps 1e-5). A checker-side number: the product
+    path never touches it."""
+    import torch as th
+    from oracle import ref_runner
+    if ref_runner.reference_dir() is None:
+        return None
+    th.set_float32_matmul_precision("high")
+    ref = ref_runner.load_reference()
+    g = th.Generator().manual_seed(5)
+    cam_o = th.nn.functional.normalize(th.randn((N_IMAGES, 3), generator=g), dim=1) * 4.0
+    cam_on = cam_o + 0.15 * th.randn((N_IMAGES, 3), generator=g)
+    n_epoch_batches = N_IMAGES * IMAGE_SIZE * IMAGE_SIZE // rays
+    model = ref_runner.build_barf(ref, N_IMAGES, SAMPLES, NEAR, FAR, n_epoch_batches, cam_o.to(dev), cam_on.to(dev),
+                                  BLUR_SIGMAS, BLUR_SIGMAS[0], alpha_epochs=ALPHA_EPOCHS).to(dev)
+    opt = th.optim.Adam(model.parameters(), lr=5e-4, eps=1e-5)
+    o = (th.nn.functional.normalize(th.randn((rays, 3), generator=g), dim=1) * 4.0).to(dev)
+    d = th.nn.functional.normalize(-o.cpu() + 0.3 * th.randn((rays, 3), generator=g), dim=1).to(dev)
+    colors = th.rand((rays, len(BLUR_SIGMAS), 3), generator=g).to(dev)
+    idx = th.randint(0, N_IMAGES, (rays,), generator=g).to(dev)
+    pw = th.full((rays,), 1 / 555.0, device=dev)
+
+    def step(s):
+        opt.zero_grad(set_to_none=True)
+        loss = model.training_step((o, o, d, d, colors, idx, pw), 100 + s)
+        loss.backward()
+        opt.step()
+    for s in range(warmup):
+        step(s)
+    th.cuda.synchronize(dev)
+    e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(steps):
+        step(warmup + s)
+    e1.record()
+    th.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    return {"ms_per_step": round(ms, 3), "rays_per_s": round(rays / ms * 1e3),
+            "what": f"unmodified reference BarfModel.training_step + backward + torch Adam on this GPU, eager PyTorch, "
+                    f"TF32 matmuls, {rays} rays x {SAMPLES} samples (oracle/_ref; CUDA events, {steps} steps after {warmup})"}
 
 
 def cpu_baseline_port(steps: int, rays: int, warmup: int = 1):
