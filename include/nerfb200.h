@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NERFB200_ABI_VERSION 4   /* 3: adam_step_dev replaces adam_step_sched; GARF fused field; render_rays; trans_cdf / prop_loss. 4: NbWgradItem z duty */
+#define NERFB200_ABI_VERSION 5   /* 3: adam_step_dev replaces adam_step_sched; GARF fused field; render_rays; trans_cdf / prop_loss. 4: NbWgradItem z duty. 5: gauss_width_grad */
 
 enum {
   NERFB200_OK = 0,
@@ -142,6 +142,20 @@ int nerfb200_trans_cdf_bwd(const float* sigma, const float* t_start, const float
 int nerfb200_prop_loss(const float* t_query, const float* cdf_query, const float* t_key,
                        const float* cdf_key, int B, int Sq, int Sk, float eps, float scale,
                        float* loss, float* d_cdf_key, void* stream);
+
+/* Gaussian-width gradients of the fused GARF networks without the pre-activation stash (a6 inside a7 / a8:
+ * the parameter gradient of barf/gaussian.py:8-63's autograd): for a layer z = W x + b followed by
+ * y = exp(-z^2 (s^2 + 1e-6)), sum over samples of z_n dz_n equals sum_c W[n,c] dW[n,c] + b_n db_n, so
+ *   d_params[g_off + n] += sign * (W[n,:] . dW[n,:] + b_n db_n) * s_n / (s_n^2 + 1e-6)
+ * from the weight / bias gradients already in d_params. The fused field calls it with sign = -1 before its
+ * weight-gradient kernel and +1 after it, so that whatever the buffer held before cancels (the map is
+ * linear). n_features = sum of out_f over the layers. */
+typedef struct {
+  int64_t w_off, b_off, g_off;   /* float offsets of weight (out_f, in_f), bias (out_f), inverse std (out_f) */
+  int32_t in_f, out_f;
+} NbGaussLayer;
+int nerfb200_gauss_width_grad(const NbGaussLayer* layers_dev, int n_layers, long long n_features,
+                              const float* params, float* d_params, float sign, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * a13. Camera extrinsics (per-image so(3) rotation + translation).

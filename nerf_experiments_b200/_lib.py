@@ -113,6 +113,10 @@ class NbWgradItem(C.Structure):
 
 WGRAD_MMA, WGRAD_COLSUM = 0, 1
 
+
+class NbGaussLayer(C.Structure):
+    _fields_ = [("w_off", C.c_int64), ("b_off", C.c_int64), ("g_off", C.c_int64), ("in_f", C.c_int32), ("out_f", C.c_int32)]
+
 # ---- mirrors of include/nerfb200_garf.h ------------------------------------------------------
 NG_MAX_OPS, NG_MAX_CHUNKS, NG_N_SLABS, NG_GEN_COLS, NG_MAX_FLOATS = 32, 6, 6, 128, 7680
 NG_MAX_PROGRAM_FLOATS = 6900   # NG_MAX_FLOATS minus the step / op tables the kernels keep in the same region
@@ -153,7 +157,7 @@ class NbAdamGroup(C.Structure):
 LR_LE_NICE, LR_EXPONENTIAL = 0, 1
 
 _lib = None
-ABI_VERSION = 4      # include/nerfb200.h: NERFB200_ABI_VERSION
+ABI_VERSION = 5      # include/nerfb200.h: NERFB200_ABI_VERSION
 
 
 def build(verbose: bool = False) -> str:
@@ -223,6 +227,7 @@ def _declare(L):
     L.nerfb200_trans_cdf_fwd.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp]
     L.nerfb200_trans_cdf_bwd.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp, vp]
     L.nerfb200_prop_loss.argtypes = [vp, vp, vp, vp, i32, i32, i32, f32, f32, vp, vp, vp]
+    L.nerfb200_gauss_width_grad.argtypes = [vp, i32, C.c_longlong, vp, vp, f32, vp]
     L.nerfb200_ray_batch.argtypes = [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, i32, i32, f32,
                                      vp, vp, vp, vp, vp, vp, vp, vp]
     L.nerfb200_kabsch.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp]
@@ -240,7 +245,7 @@ EXPORTS = [
     "nerfb200_pose_fwd", "nerfb200_pose_bwd", "nerfb200_so3_to_SO3",
     "nerfb200_mlp_pack", "nerfb200_mlp_fwd", "nerfb200_mlp_fwd2", "nerfb200_mlp_bwd", "nerfb200_mlp_wgrad", "nerfb200_pe_fwd", "nerfb200_pe_bwd",
     "nerfb200_mlp_workspace_bytes", "nerfb200_garf_workspace_bytes", "nerfb200_garf_fwd", "nerfb200_garf_bwd",
-    "nerfb200_render_rays_workspace_bytes", "nerfb200_render_rays", "nerfb200_lindisp_intervals", "nerfb200_trans_cdf_fwd", "nerfb200_trans_cdf_bwd", "nerfb200_prop_loss",
+    "nerfb200_render_rays_workspace_bytes", "nerfb200_render_rays", "nerfb200_lindisp_intervals", "nerfb200_trans_cdf_fwd", "nerfb200_trans_cdf_bwd", "nerfb200_prop_loss", "nerfb200_gauss_width_grad",
     "nerfb200_adam_step", "nerfb200_adam_step_dev", "nerfb200_act_fwd", "nerfb200_act_bwd", "nerfb200_ray_batch", "nerfb200_kabsch",
 ]
 

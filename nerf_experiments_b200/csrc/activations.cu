@@ -164,7 +164,52 @@ int launch_shape(long long N, int F, dim3& grid, int& rows_per_block) {
 }  // namespace
 }  // namespace nerfb200
 
+namespace nerfb200 {
+namespace {
+// Gradient of the Gaussian widths of a layer z = W x + b, y = exp(-z^2 (s^2 + 1e-6)) WITHOUT the
+// pre-activations: sum over samples of z_n dz_n = sum_c W[n,c] dW[n,c] + b_n db_n (dW = dz^T x, db = sum dz),
+// and dL/ds_n = (sum_samples z_n dz_n) s_n / (s_n^2 + 1e-6) (dz = -2 v z y g). One warp per output feature.
+__global__ void __launch_bounds__(256) gauss_width_grad_kernel(const NbGaussLayer* layers, int n_layers,
+                                                               const float* params, float* d_params, float sign) {
+  const int lane = threadIdx.x & 31;
+  long long feat = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int l = 0;
+  for (; l < n_layers; ++l) {
+    if (feat < layers[l].out_f) break;
+    feat -= layers[l].out_f;
+  }
+  if (l >= n_layers) return;
+  const NbGaussLayer L = layers[l];
+  const float* W = params + L.w_off + feat * L.in_f;
+  const float* dW = d_params + L.w_off + feat * L.in_f;
+  float acc = 0.f;
+  for (int c = lane; c < L.in_f; c += 32) acc = fmaf(__ldg(W + c), dW[c], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    acc = fmaf(params[L.b_off + feat], d_params[L.b_off + feat], acc);
+    const float sdev = params[L.g_off + feat];
+    d_params[L.g_off + feat] += sign * acc * sdev / (sdev * sdev + 1e-6f);
+  }
+}
+}  // namespace
+}  // namespace nerfb200
+
 using namespace nerfb200;
+
+extern "C" int nerfb200_gauss_width_grad(const NbGaussLayer* layers_dev, int n_layers, long long n_features,
+                                         const float* params, float* d_params, float sign, void* stream) {
+  NB_CHECK_ARG(n_layers >= 0 && n_features >= 0 && (n_layers == 0 || (layers_dev && params && d_params)),
+               "gauss_width_grad: bad arguments");
+  if (n_layers == 0 || n_features == 0) return NERFB200_OK;
+  const int warps = 8;
+  const long long blocks = (n_features + warps - 1) / warps;
+  gauss_width_grad_kernel<<<(unsigned)blocks, warps * 32, 0, (cudaStream_t)stream>>>(layers_dev, n_layers, params,
+                                                                                     d_params, sign);
+  count_launch();
+  NB_CHECK_LAUNCH();
+  return NERFB200_OK;
+}
+
 
 extern "C" int nerfb200_act_fwd(int kind, const float* x, const float* p0, const float* p1,
                                 long long N, int F, void* y, int out_bf16, void* stream) {

@@ -8,7 +8,7 @@ from typing import Optional
 import torch as th
 
 from . import _lib
-from ._lib import NbPackBias, NbPackChunk, NbWgradItem, check, lib
+from ._lib import NbGaussLayer, NbPackBias, NbPackChunk, NbWgradItem, check, lib
 from .fused_mlp import FlatParams, make_inputs
 from .mlp_program import schedule_wgrad, to_device_array
 
@@ -43,6 +43,10 @@ class FusedGarfField:
             self.fdesc_bwd = to_device_array(cg.bwd_floats, NbPackBias, device)
             self._wgrad_items = {}
             self._packed_sig = None
+            gl = [NbGaussLayer(w_off=l.lin.w_off, b_off=l.lin.b_off, g_off=l.g_off, in_f=l.lin.in_f, out_f=l.lin.out_f)
+                  for l in cg.gauss_layers]
+            self.gauss_dev = to_device_array(gl, NbGaussLayer, device) if gl else None
+            self.n_gauss_layers, self.n_gauss_features = len(gl), sum(l.out_f for l in gl)
         sig = self.flat.signature()
         if sig != self._packed_sig:
             cg = self.compiled
@@ -109,10 +113,18 @@ class FusedGarfField:
                 None if samples_mode else _ptr(d_a), None if samples_mode else _ptr(d_b),
                 _ptr(d_a) if samples_mode else None, _ptr(d_b) if samples_mode else None, stream), "garf_bwd"))
             items_dev, n_items = self._items(n_tiles)
+            # Gaussian widths: d s = (W . dW + b db) s / (s^2 + 1e-6) from THIS call's dW, db — whatever the
+            # gradient buffer already holds is subtracted before the weight-gradient kernel and added back after
+            width = lambda sign: check(lib().nerfb200_gauss_width_grad(
+                _ptr(self.gauss_dev), self.n_gauss_layers, self.n_gauss_features, _ptr(self.flat.flat), _ptr(flat_grad),
+                sign, stream), "gauss_width_grad")
+            if self.flat.grad_sink is not None:
+                width(-1.0)
             self._timed("garf_wgrad", lambda: check(lib().nerfb200_mlp_wgrad(
                 _ptr(items_dev), n_items, _ptr(y_stash), cg.fwd.y_slabs_per_tile, _ptr(dy_stash),
                 cg.bwd.y_slabs_per_tile, _ptr(z_stash), cg.fwd.z_slabs_per_tile, _ptr(self.flat.flat),
                 _ptr(flat_grad), stream), "mlp_wgrad"))
+            width(1.0)
         return flat_grad, d_a, d_b
 
 

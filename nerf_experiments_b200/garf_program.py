@@ -42,6 +42,7 @@ class CompiledGarf:
     has_rgb: bool
     macs_per_sample: int
     gauss_per_sample: int
+    gauss_layers: List = field(default_factory=list)   # GaussLinear layers whose width gradient follows from dW and db
 
 
 class _Builder:
@@ -208,46 +209,24 @@ def _mma_bwd(b: _Builder, lin: Linear, a_slabs, k_outs, in0, n_in, tmem_col, acc
     b.op(a_slabs, k16s, offs, n_pad, [(tmem_col, n_pad, 0)], accumulate)
 
 
-WGRAD_STAGE_HALF_SLABS = 9      # csrc/mlp_wgrad.cu: half slabs of one pipeline stage
-
-
 def _colsum_units(units, dy0, z0, layer: GaussLinear):
-    """Bias and Gaussian-width gradients of one layer (sum dz, sum z*dz per column): a "z duty" that rides on
-    the weight units already streaming the layer's dz slabs wherever their pipeline stage has room for
-    the z slabs (2*ceil(n_dy/2) + n_x + n_z <= 9 half slabs); what is left becomes column-sum-only units.
-    Must be called after the layer's weight units have been appended."""
+    """Bias gradient of a Gaussian layer (column sums of its dz slabs): rides on ONE weight unit per group of dz
+    slabs, as for the ReLU network. The width gradient needs no pass over the samples at all: sum z dz =
+    W . dW + b db per output feature (include/nerfb200.h, nerfb200_gauss_width_grad), so the weight-gradient
+    kernel never reads the z stash. Must be called after the layer's weight units have been appended."""
     n_slabs = _ceil(layer.lin.out_f, 64)
-    todo = [True] * n_slabs                       # dz slab dy0 + s still needs its sums
+    todo = [True] * n_slabs
     for u in units:
-        if u.mode != _lib.WGRAD_MMA or u.n_z_slabs or u.bias_dst >= 0:
+        if u.mode != _lib.WGRAD_MMA or u.bias_dst >= 0:
             continue
         lo, hi = u.dy_slab - dy0, u.dy_slab - dy0 + u.n_dy_slabs
-        if lo < 0 or hi > n_slabs:
+        if lo < 0 or hi > n_slabs or not all(todo[lo:hi]):
             continue
-        room = WGRAD_STAGE_HALF_SLABS - 2 * _ceil(u.n_dy_slabs, 2) - u.n_x_slabs
-        run = [s for s in range(lo, hi) if todo[s]]
-        if room <= 0 or not run:
-            continue
-        first = run[0]
-        n = 0
-        while n < room and first + n < hi and todo[first + n]:
-            n += 1
-        for s in range(first, first + n):
+        u.bias_dst = layer.lin.b_off + 64 * lo
+        for s in range(lo, hi):
             todo[s] = False
-        u.z_slab, u.n_z_slabs, u.z_first = z0 + first, n, first - lo
-        u.zbias_dst, u.coef_dst = layer.lin.b_off + 64 * lo, layer.g_off + 64 * lo
-    s = 0
-    while s < n_slabs:
-        if not todo[s]:
-            s += 1
-            continue
-        n = 1
-        while n < 4 and s + n < n_slabs and todo[s + n]:
-            n += 1
-        m = min(64 * n, layer.lin.out_f - 64 * s)
-        units.append(WgradUnit(dy0 + s, n, 0, 0, m, 0, 0, 0, mode=_lib.WGRAD_COLSUM, coef_dst=layer.g_off + 64 * s,
-                               z_slab=z0 + s, n_z_slabs=n, z_first=0, zbias_dst=layer.lin.b_off + 64 * s))
-        s += n
+    if any(todo):
+        raise RuntimeError("GARF program: a dz slab without a weight unit to carry its bias gradient")
 
 
 def _weight_units(units, lin: Linear, dy0, n_out, x0, in0, n_in, bias=False, out0=0):
@@ -383,7 +362,8 @@ def compile_radiance(L: List[GaussLinear], Lc: List[GaussLinear]) -> CompiledGar
     macs = sum(l.lin.in_f * l.lin.out_f for l in L + Lc)
     gauss = sum(l.lin.out_f for l in L + Lc if l.g_off >= 0)
     return CompiledGarf(fwd=fwd, bwd=bwd, pack_chunks=f.chunks + g.chunks, fwd_floats=f.floats, bwd_floats=g.floats,
-                        wpack_units=g.w_units, units=units, has_rgb=True, macs_per_sample=macs, gauss_per_sample=gauss)
+                        wpack_units=g.w_units, units=units, has_rgb=True, macs_per_sample=macs, gauss_per_sample=gauss,
+                        gauss_layers=[l for l in L + Lc if l.g_off >= 0])
 
 
 def _first_layer_bwd(g: _Builder, L1: GaussLinear, L2: GaussLinear, z1: int, d_1: int):
@@ -468,4 +448,5 @@ def compile_proposal(L: List[GaussLinear]) -> CompiledGarf:
     macs = sum(l.lin.in_f * l.lin.out_f for l in L)
     gauss = sum(l.lin.out_f for l in L if l.g_off >= 0)
     return CompiledGarf(fwd=fwd, bwd=bwd, pack_chunks=f.chunks + g.chunks, fwd_floats=f.floats, bwd_floats=g.floats,
-                        wpack_units=g.w_units, units=units, has_rgb=False, macs_per_sample=macs, gauss_per_sample=gauss)
+                        wpack_units=g.w_units, units=units, has_rgb=False, macs_per_sample=macs, gauss_per_sample=gauss,
+                        gauss_layers=[l for l in L if l.g_off >= 0])

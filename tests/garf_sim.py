@@ -231,4 +231,12 @@ def run_network(cg, params, pos, dirs, g_sigma, g_rgb):
             rgb_out[t0: t0 + nv] = rgb[:nv]
         dpos_out[t0: t0 + nv] = dp[:nv]
         ddir_out[t0: t0 + nv] = dd[:nv]
+    # Gaussian widths from the weight / bias gradients (nerfb200_gauss_width_grad): sum z dz = W . dW + b db
+    for layer in cg.gauss_layers:
+        lin = layer.lin
+        W = params[lin.w_off: lin.w_off + lin.out_f * lin.in_f].view(lin.out_f, lin.in_f)
+        dW = grad[lin.w_off: lin.w_off + lin.out_f * lin.in_f].view(lin.out_f, lin.in_f)
+        b, db = params[lin.b_off: lin.b_off + lin.out_f], grad[lin.b_off: lin.b_off + lin.out_f]
+        sdev = params[layer.g_off: layer.g_off + lin.out_f]
+        grad[layer.g_off: layer.g_off + lin.out_f] += ((W * dW).sum(1) + b * db) * sdev / (sdev * sdev + 1e-6)
     return sig_out, (rgb_out if cg.has_rgb else None), grad, dpos_out, ddir_out

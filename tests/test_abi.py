@@ -28,7 +28,7 @@ def test_library_builds_and_exports_every_declared_symbol():
 def test_abi_version_and_error_channel():
     from nerf_experiments_b200 import _lib
     L = _lib.lib()
-    assert L.nerfb200_abi_version() == 4
+    assert L.nerfb200_abi_version() == 5
     # argument validation happens before any CUDA call: callable without a GPU
     rc = L.nerfb200_composite_fwd(None, None, None, None, 4, 8, 0, None, None, None, None, None)
     assert rc == 1
@@ -45,9 +45,9 @@ def test_struct_sizes_match_the_header():
     src = r'''
 #include <stdio.h>
 #include "nerfb200.h"
-int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(NbBlock), sizeof(NbOp), sizeof(NbProgram),
+int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(NbBlock), sizeof(NbOp), sizeof(NbProgram),
   sizeof(NbPeCfg), sizeof(NbMlpInputs), sizeof(NbPackChunk), sizeof(NbPackBias), sizeof(NbWgradItem),
-  sizeof(NgStep), sizeof(NgBlock), sizeof(NgOp), sizeof(NgProgram), sizeof(NbAdamGroup)); return 0; }
+  sizeof(NgStep), sizeof(NgBlock), sizeof(NgOp), sizeof(NgProgram), sizeof(NbAdamGroup), sizeof(NbGaussLayer)); return 0; }
 '''
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "s.c")
@@ -56,7 +56,7 @@ int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n",
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
     mirrors = [_lib.NbBlock, _lib.NbOp, _lib.NbProgram, _lib.NbPeCfg, _lib.NbMlpInputs, _lib.NbPackChunk,
-               _lib.NbPackBias, _lib.NbWgradItem, _lib.NgStep, _lib.NgBlock, _lib.NgOp, _lib.NgProgram, _lib.NbAdamGroup]
+               _lib.NbPackBias, _lib.NbWgradItem, _lib.NgStep, _lib.NgBlock, _lib.NgOp, _lib.NgProgram, _lib.NbAdamGroup, _lib.NbGaussLayer]
     assert sizes == [ctypes.sizeof(m) for m in mirrors]
 
 
