@@ -484,16 +484,23 @@ def compile_backward(cm: CompiledMlp, want_input_grads: bool, encoders=None) -> 
                             bias_map=bias_map, units=units)
 
 
-def schedule_wgrad(units: List[WgradUnit], n_tiles: int, n_workers: int):
+def schedule_wgrad(units: List[WgradUnit], n_tiles: int, n_workers: int, per_worker: Optional[float] = None):
     """Splits every unit over tile ranges so that ~3 items per worker of similar cost result;
     returns NbWgradItem structs sorted by decreasing cost (static round-robin in the kernel).
     The kernel is HBM-bound, so an SM idling at the end of the launch is lost bandwidth, while
     every item costs a pipeline fill and a TMEM flush: measured on the bench workload (4096
     tiles, 148 SMs) 1 / 2 / 3 / 4 / 6 / 8 items per worker take 1.55 / 1.29 / 1.13 / 1.19 / 1.19 /
-    1.37 ms (a longest-first assignment of the same items is no better)."""
+    1.37 ms (a longest-first assignment of the same items is no better). Round 2, GARF radiance network
+    (6144 tiles, 22 units of cost 5 .. 8 slabs per tile): 2 / 3 / 4 / 6 / 8 / 10 / 16 items per worker take
+    2.50 / 2.60 / 2.18 / 1.98 / 2.03 / 2.12 / 2.21 ms, and an equal-bytes partition with one or two LARGE items
+    per worker is the slowest of all (2.77 ms; 1.49 ms on the ReLU network): what matters is that the
+    accumulator flushes of the workers are spread over the launch instead of meeting at its end, so the
+    callers pass `per_worker` ~ streamed bytes / (workers x 14 MB), at least 3."""
     import os
     from ._lib import NbWgradItem
-    per_worker = float(os.environ.get("NB_WGRAD_ITEMS_PER_WORKER", "3"))   # the env knob is for experiments
+    if per_worker is None:
+        per_worker = 3.0
+    per_worker = float(os.environ.get("NB_WGRAD_ITEMS_PER_WORKER", per_worker))   # the env knob is for experiments
     cost = [(u.n_dy_slabs + u.n_x_slabs + u.n_z_slabs) for u in units]
     total = sum(cost) * n_tiles
     target = max(total / max(per_worker * n_workers, 1), 1.0)
