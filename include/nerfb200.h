@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NERFB200_ABI_VERSION 5   /* 3: adam_step_dev replaces adam_step_sched; GARF fused field; render_rays; trans_cdf / prop_loss. 4: NbWgradItem z duty. 5: gauss_width_grad */
+#define NERFB200_ABI_VERSION 6   /* 3: adam_step_dev replaces adam_step_sched; GARF fused field; render_rays; trans_cdf / prop_loss. 4: NbWgradItem z duty. 5: gauss_width_grad. 6: NbWgradItem.x2_slab */
 
 enum {
   NERFB200_OK = 0,

@@ -187,6 +187,10 @@ typedef struct {
   int32_t n_z_slabs;            /* 0..4                                                        */
   int32_t z_first;              /* index (within the item) of the dY slab of z slab 0          */
   int32_t zbias_dst;            /* float index of the bias gradient of output feature m0, -1   */
+  int32_t x2_slab;              /* >= 0: the item's LAST X slab is stash slab x2_slab instead  */
+                                /* of x_slab + n_x_slabs - 1 (a concatenating layer whose two  */
+                                /* input sources sit apart in the stash: one item, dY read     */
+                                /* once); -1: the X slabs are consecutive                      */
 } NbWgradItem;
 enum { NB_WGRAD_MMA = 0, NB_WGRAD_COLSUM = 1 };
 

@@ -99,7 +99,8 @@ class NbWgradItem(C.Structure):
                 ("n_x_slabs", C.c_int32), ("dy_slab", C.c_int32), ("x_slab", C.c_int32),
                 ("m_real", C.c_int32), ("n_real", C.c_int32), ("dst", C.c_int64), ("ld", C.c_int32),
                 ("bias_dst", C.c_int32), ("mode", C.c_int32), ("coef_dst", C.c_int32),
-                ("z_slab", C.c_int32), ("n_z_slabs", C.c_int32), ("z_first", C.c_int32), ("zbias_dst", C.c_int32)]
+                ("z_slab", C.c_int32), ("n_z_slabs", C.c_int32), ("z_first", C.c_int32), ("zbias_dst", C.c_int32),
+                ("x2_slab", C.c_int32)]
 
     def __init__(self, *args, **kw):
         kw.setdefault("mode", 0)
@@ -108,6 +109,7 @@ class NbWgradItem(C.Structure):
         kw.setdefault("n_z_slabs", 0)
         kw.setdefault("z_first", 0)
         kw.setdefault("zbias_dst", -1)
+        kw.setdefault("x2_slab", -1)
         super().__init__(*args, **kw)
 
 
@@ -157,7 +159,7 @@ class NbAdamGroup(C.Structure):
 LR_LE_NICE, LR_EXPONENTIAL = 0, 1
 
 _lib = None
-ABI_VERSION = 5      # include/nerfb200.h: NERFB200_ABI_VERSION
+ABI_VERSION = 6      # include/nerfb200.h: NERFB200_ABI_VERSION
 
 
 def build(verbose: bool = False) -> str:

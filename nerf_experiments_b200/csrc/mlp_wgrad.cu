@@ -92,9 +92,12 @@ mlp_wgrad_kernel(const __grid_constant__ WgradParams p) {
             for (int s = 0; s < item.n_dy_slabs; ++s)
               bulk_g2s(dst + s * kHalfSlabBytes, dy + (size_t)s * NB_SLAB_BYTES + half * kHalfSlabBytes,
                        kHalfSlabBytes, &full[stage]);
-            for (int s = 0; s < n_x; ++s)
-              bulk_g2s(dst + (pos_x + s) * kHalfSlabBytes, x + (size_t)s * NB_SLAB_BYTES + half * kHalfSlabBytes,
-                       kHalfSlabBytes, &full[stage]);
+            for (int s = 0; s < n_x; ++s) {
+              const uint8_t* xs = (s == n_x - 1 && item.x2_slab >= 0)
+                  ? p.x_stash + ((size_t)tile * p.x_slabs_per_tile + item.x2_slab) * NB_SLAB_BYTES
+                  : x + (size_t)s * NB_SLAB_BYTES;
+              bulk_g2s(dst + (pos_x + s) * kHalfSlabBytes, xs + half * kHalfSlabBytes, kHalfSlabBytes, &full[stage]);
+            }
             for (int s = 0; s < n_z; ++s)
               bulk_g2s(dst + (pos_z + s) * kHalfSlabBytes, z + (size_t)s * NB_SLAB_BYTES + half * kHalfSlabBytes,
                        kHalfSlabBytes, &full[stage]);

@@ -88,9 +88,9 @@ class FusedGarfField:
     def _items(self, n_tiles: int):
         if n_tiles not in self._wgrad_items:
             n_sm = th.cuda.get_device_properties(self.device).multi_processor_count
-            # items of ~14 MB of streamed slabs each (mlp_program.schedule_wgrad: measured), at least 3 per SM
+            # items of ~20 MB of streamed slabs each (mlp_program.schedule_wgrad: measured), at least 3 per SM
             slabs = sum(u.n_dy_slabs + u.n_x_slabs + u.n_z_slabs for u in self.compiled.units) * n_tiles
-            per_worker = min(max(round(slabs * _lib.NB_SLAB_BYTES / (n_sm * 14e6)), 3), 8)
+            per_worker = min(max(round(slabs * _lib.NB_SLAB_BYTES / (n_sm * 20e6)), 3), 8)
             items = schedule_wgrad(self.compiled.units, n_tiles, n_sm, per_worker)
             self._wgrad_items[n_tiles] = (to_device_array(items, NbWgradItem, self.device), len(items))
         return self._wgrad_items[n_tiles]

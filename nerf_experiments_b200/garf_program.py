@@ -241,6 +241,18 @@ def _weight_units(units, lin: Linear, dy0, n_out, x0, in0, n_in, bias=False, out
                                    bias_dst=(lin.b_off + out0 + 256 * u) if first else -1))
 
 
+def _weight_units_concat(units, lin: Linear, dy0, n_out, x0, n_main, x_extra, n_extra):
+    """A concatenating layer [main (n_main columns, X slabs x0..) | extra (n_extra <= 64 columns, slab x_extra)] as ONE
+    unit per 256 output features: the extra slab rides as the unit's last X slab (NbWgradItem.x2_slab), so the dY
+    slabs are streamed once instead of once per source."""
+    if n_main % 64 or n_main + 64 > 256 or n_extra > 64 or lin.in_f != n_main + n_extra:
+        raise RuntimeError("concatenating layer does not fit one weight-gradient unit")
+    for u in range(_ceil(n_out, 256)):
+        m = min(256, n_out - 256 * u)
+        units.append(WgradUnit(dy0 + 4 * u, _ceil(m, 64), x0, n_main // 64 + 1, m, n_main + n_extra,
+                               lin.w_off + 256 * u * lin.in_f, lin.in_f, x2_slab=x_extra))
+
+
 def compile_radiance(L: List[GaussLinear], Lc: List[GaussLinear]) -> CompiledGarf:
     """L = [L1 (3->1024 G), L2 (1024->256 G), L3 (256->128 G), L4 (128->128 G), L5 (131->512 G),
     L6 (512->256 G), L7 (256->128 G), L8 (128->129)], Lc = [C1 (131->256 G), C2 (256->3)]
@@ -347,14 +359,12 @@ def compile_radiance(L: List[GaussLinear], Lc: List[GaussLinear]) -> CompiledGar
     _weight_units(units, L2.lin, d_2, 256, y1, 0, 1024)
     _weight_units(units, L3.lin, d_3, 128, y2, 0, 256)
     _weight_units(units, L4.lin, d_4, 128, y3, 0, 128)
-    _weight_units(units, L5.lin, d_5, 512, y4, 0, 128)
-    _weight_units(units, L5.lin, d_5, 512, aux_pos, 128, 3)
+    _weight_units_concat(units, L5.lin, d_5, 512, y4, 128, aux_pos, 3)
     _weight_units(units, L6.lin, d_6, 256, y5, 0, 512)
     _weight_units(units, L7.lin, d_7, 128, y6, 0, 256)
     _weight_units(units, L8.lin, d_8, 128, y7, 0, 128, bias=True)
     _weight_units(units, L8.lin, d_8 + 2, 1, y7, 0, 128, bias=True, out0=128)
-    _weight_units(units, C1.lin, d_c1, 256, ysum, 0, 128)
-    _weight_units(units, C1.lin, d_c1, 256, aux_dir, 128, 3)
+    _weight_units_concat(units, C1.lin, d_c1, 256, ysum, 128, aux_dir, 3)
     _weight_units(units, C2.lin, d_head, 3, yc1, 0, 256, bias=True)
     for layer, dy0, zz in ((L1, d_1, z1), (L2, d_2, z2), (L3, d_3, z3), (L4, d_4, z4), (L5, d_5, z5), (L6, d_6, z6),
                            (L7, d_7, z7), (C1, d_c1, zc1)):

@@ -301,6 +301,7 @@ class WgradUnit:
     n_z_slabs: int = 0     # float index of the bias gradient of the first feature
     z_first: int = 0
     zbias_dst: int = -1
+    x2_slab: int = -1      # >= 0: the LAST X slab comes from this stash slab (two input sources, one unit)
 
 
 @dataclass
@@ -494,8 +495,11 @@ def schedule_wgrad(units: List[WgradUnit], n_tiles: int, n_workers: int, per_wor
     (6144 tiles, 22 units of cost 5 .. 8 slabs per tile): 2 / 3 / 4 / 6 / 8 / 10 / 16 items per worker take
     2.50 / 2.60 / 2.18 / 1.98 / 2.03 / 2.12 / 2.21 ms, and an equal-bytes partition with one or two LARGE items
     per worker is the slowest of all (2.77 ms; 1.49 ms on the ReLU network): what matters is that the
-    accumulator flushes of the workers are spread over the launch instead of meeting at its end, so the
-    callers pass `per_worker` ~ streamed bytes / (workers x 14 MB), at least 3."""
+    accumulator flushes of the workers are spread over the launch instead of meeting at its end. The jagged
+    curve came from the static round-robin handing worker 0 the largest item of every round; with every other
+    round reversed (below) it is smooth — 2 / 3 / 4 / 5 / 6 / 8 items: 2.90 / 2.02 / 1.85 / 1.87 / 1.89 / 1.93 ms
+    (after the concatenating layers' units were merged) — so the GARF fields pass `per_worker` ~ streamed bytes /
+    (workers x 20 MB), at least 3; the ReLU network stays at 3 (1.08 ms either way)."""
     import os
     from ._lib import NbWgradItem
     if per_worker is None:
@@ -519,6 +523,12 @@ def schedule_wgrad(units: List[WgradUnit], n_tiles: int, n_workers: int, per_wor
                                                          m_real=u.m_real, n_real=u.n_real, dst=u.dst, ld=u.ld,
                                                          bias_dst=u.bias_dst, mode=u.mode, coef_dst=u.coef_dst,
                                                          z_slab=u.z_slab, n_z_slabs=u.n_z_slabs, z_first=u.z_first,
-                                                         zbias_dst=u.zbias_dst)))
+                                                         zbias_dst=u.zbias_dst, x2_slab=u.x2_slab)))
     items.sort(key=lambda t: -t[0])
+    if os.environ.get("NB_WGRAD_SNAKE", "1") == "1":
+        # The kernel hands item i to worker i mod n_workers: with the items sorted by decreasing cost, worker 0
+        # would get the largest item of EVERY round. Reversing every other round (boustrophedon) pairs a
+        # worker's large item of one round with a small one of the next.
+        for r in range(1, (len(items) + n_workers - 1) // n_workers, 2):
+            items[r * n_workers: (r + 1) * n_workers] = items[r * n_workers: (r + 1) * n_workers][::-1]
     return [it for _, it in items]

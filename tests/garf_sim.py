@@ -197,7 +197,10 @@ def weight_gradients(units, params, grad, y_stash, dy_stash, z_stash):
                 grad[u.coef_dst + c0: u.coef_dst + c1] += (zv * dyv[:, c0:c1]).sum(0) * s / (s * s + 1e-6)
         if u.mode == _lib.WGRAD_COLSUM:
             continue
-        xv = th.cat([y_stash[u.x_slab + j] for j in range(u.n_x_slabs)], dim=1)[:, :u.n_real]
+        xs = [u.x_slab + j for j in range(u.n_x_slabs)]
+        if u.x2_slab >= 0:
+            xs[-1] = u.x2_slab
+        xv = th.cat([y_stash[j] for j in xs], dim=1)[:, :u.n_real]
         dw = dyv.T @ xv                                                       # (m_real, n_real)
         for m in range(u.m_real):
             grad[u.dst + m * u.ld: u.dst + m * u.ld + u.n_real] += dw[m]

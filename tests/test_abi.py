@@ -28,7 +28,7 @@ def test_library_builds_and_exports_every_declared_symbol():
 def test_abi_version_and_error_channel():
     from nerf_experiments_b200 import _lib
     L = _lib.lib()
-    assert L.nerfb200_abi_version() == 5
+    assert L.nerfb200_abi_version() == 6
     # argument validation happens before any CUDA call: callable without a GPU
     rc = L.nerfb200_composite_fwd(None, None, None, None, 4, 8, 0, None, None, None, None, None)
     assert rc == 1
