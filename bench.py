@@ -276,10 +276,13 @@ def run_ours(args):
     traffic, traffic_source = None, None
     try:
         import glob
-        newest = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))[-1]
-        prof = json.load(open(newest))
         kname = {"mlp_fwd_train": "mlp_fwd_kernel", "mlp_bwd_inputs": "mlp_bwd_kernel", "mlp_bwd": "mlp_bwd_kernel",
                  "mlp_wgrad": "mlp_wgrad_kernel"}[top]
+        # the newest capture of THIS workload (the GARF captures under the same naming hold a list of launches)
+        cands = [f for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
+                 if isinstance(json.load(open(f)).get("kernels"), dict)]
+        newest = cands[-1]
+        prof = json.load(open(newest))
         rec = prof["kernels"][kname]
         traffic = rec["dram_bytes_read"] + rec["dram_bytes_write"]
         traffic_source = "profiles/" + os.path.basename(newest) + " (ncu --set full capture, not this run)"
