@@ -195,6 +195,12 @@ def run_ours(args):
     # device-resident batches in the layout of the graph's inputs: a step is one device copy + one graph launch
     packed = [eng.pack_batch(batches[W + N_PROFILE + i]) for i in range(K)]
     barrier()
+    # warm-up of the measured path itself, right in front of the timed region: W replays of the captured step
+    # (the GPUs idled while the host packed the batches; at N = 8 the first replays after that gap ran ~7 %
+    # slower than the same replays later in the run)
+    for i in range(max(W, 3)):
+        eng.replay_packed(packed[i % K])
+    barrier()
 
     # ---- device-resident timed region: K graph replays -------------------------------------------
     # clocks / throttle reasons are sampled from here to the end of the end-to-end region below
