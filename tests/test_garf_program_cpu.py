@@ -116,3 +116,81 @@ def test_program_invariants():
                 for c in range(op.n_chunks):
                     readers[op.a_slab[c]] = k
     assert cg.fwd.n_floats <= _lib.NG_MAX_PROGRAM_FLOATS and cg.bwd.n_floats <= _lib.NG_MAX_PROGRAM_FLOATS
+
+
+def _compiled_networks():
+    from nerf_experiments_b200.model_garf_proposal import ProposalNetwork
+    from nerf_experiments_b200.model_garf_radiance import RadianceNetwork
+    th.manual_seed(1)
+    out = []
+    for net in (RadianceNetwork(0.5, 1.5), ProposalNetwork(0.5, 1.5)):
+        f = net.fused_field()
+        out.append((net, f, f.compile_fn(f.flat)))
+    return out
+
+
+def test_early_ops_never_write_the_columns_their_step_reads():
+    """NgOp.early (the op's MMAs start slab by slab under the epilogue of the step in front of it) is only set
+    where the op's accumulator blocks are disjoint from the columns that step still reads, and every Gaussian
+    step that publishes slabs got it (the TMEM regions of consecutive layers alternate for that)."""
+    from nerf_experiments_b200 import _lib
+    for _, _, cg in _compiled_networks():
+        for prog in (cg.fwd, cg.bwd):
+            for k in range(prog.n_ops):
+                st, op = prog.steps[k], prog.ops[k]
+                publishes = st.kind in (_lib.NG_STEP_ACT, _lib.NG_BSTEP_ACT) and st.out_slab >= 0 and \
+                    not (st.flags & _lib.NG_F_DIRECT) and op.n_chunks > 0
+                assert bool(op.early) == publishes, (k, st.kind, op.early)
+                if op.early:
+                    lo, hi = st.src_col, st.src_col + 64 * st.n_slabs
+                    for b in range(op.n_blocks):
+                        c0, c1 = op.blocks[b].tmem_col, op.blocks[b].tmem_col + op.blocks[b].n
+                        assert c1 <= lo or hi <= c0, (k, (lo, hi), (c0, c1))
+
+
+def test_weight_gradient_units_cover_every_parameter_once():
+    """Every weight element belongs to exactly one unit, every bias (= every dz slab's column sums) to exactly
+    one unit, a concatenating layer is ONE unit per 256 output features (x2_slab), no unit reads the z stash,
+    and every Gaussian layer is listed for nerfb200_gauss_width_grad."""
+    from nerf_experiments_b200 import _lib
+    for net, f, cg in _compiled_networks():
+        n_params = f.flat.numel
+        w_cover, b_cover = th.zeros(n_params, dtype=th.int32), th.zeros(n_params, dtype=th.int32)
+        for u in cg.units:
+            assert u.mode == _lib.WGRAD_MMA and u.n_z_slabs == 0 and u.z_slab < 0
+            assert 2 * ((u.n_dy_slabs + 1) // 2) + u.n_x_slabs <= 9 and u.n_real <= 64 * u.n_x_slabs
+            for m in range(u.m_real):
+                w_cover[u.dst + m * u.ld: u.dst + m * u.ld + u.n_real] += 1
+            if u.bias_dst >= 0:
+                b_cover[u.bias_dst: u.bias_dst + u.m_real] += 1
+        n_gauss = 0
+        for name, p in net.named_parameters():
+            o = f.flat.offset_of(p)
+            if name.endswith("weight"):
+                assert bool((w_cover[o: o + p.numel()] == 1).all()), name
+            elif name.endswith("bias"):
+                assert bool((b_cover[o: o + p.numel()] == 1).all()), name
+            else:
+                n_gauss += p.numel()
+                assert any(l.g_off == o and l.lin.out_f == p.numel() for l in cg.gauss_layers), name
+        assert n_gauss == sum(l.lin.out_f for l in cg.gauss_layers) == cg.gauss_per_sample
+    rad_units = _compiled_networks()[0][2].units
+    assert sum(1 for u in rad_units if u.x2_slab >= 0) == 3          # 131 -> 512 (two units) and 131 -> 256
+
+
+def test_weight_gradient_schedule_covers_every_tile_once():
+    """schedule_wgrad: the items of a unit tile its range exactly once, whatever the number of items per
+    worker; the boustrophedon order only permutes them."""
+    from nerf_experiments_b200.mlp_program import schedule_wgrad
+    cg = _compiled_networks()[0][2]
+    for n_tiles, per_worker in ((6144, 4), (37, 3), (1, 8)):
+        items = schedule_wgrad(cg.units, n_tiles, 148, per_worker)
+        cover = {}
+        for it in items:
+            key = (it.dy_slab, it.x_slab, it.x2_slab, it.dst)
+            cover.setdefault(key, []).append((it.tile_begin, it.tile_end))
+        assert len(cover) == len(cg.units)
+        for spans in cover.values():
+            spans.sort()
+            assert spans[0][0] == 0 and spans[-1][1] == n_tiles
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
