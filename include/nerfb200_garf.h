@@ -77,7 +77,9 @@ typedef struct {
   int8_t flags;
   int8_t reserved;
   int16_t src_col;          /* first accumulator (TMEM) column read                             */
-  int16_t sigma_col;        /* TMEM column of the density pre-activation (NG_F_SIGMA, forward)  */
+  int16_t sigma_col;        /* forward: TMEM column of the density pre-activation (NG_F_SIGMA);  */
+                            /* backward: first of the 64 TMEM columns in which NG_F_HOLD_SAVE    */
+                            /* parks the residual-path gradient for the NG_F_HOLD_ADD step        */
   int32_t bias_off;         /* packed floats: bias[64 * n_slabs]              (-1: none)        */
   int32_t coef_off;         /* packed floats: Gaussian coefficient -(1/s^2 + 1e-6) log2(e)      */
   int32_t skip_off;         /* packed floats: skip weights, [3][64 * n_slabs]  (-1: none)        */

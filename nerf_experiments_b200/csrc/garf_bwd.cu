@@ -105,11 +105,6 @@ garf_bwd_kernel(const __grid_constant__ GarfBwdParams p) {
         tq = p.in.t_mode == 0 ? ps.t0 : (ps.t0 + ps.t1) * 0.5f;
       }
       float dpos[3] = {0.f, 0.f, 0.f}, ddir[3] = {0.f, 0.f, 0.f};
-      uint32_t hold[2][8];
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) hold[j][i] = 0u;
 
       for (int k = 0; k <= n_ops; ++k) {
         const NgStep& st = sm.steps[k];
@@ -177,8 +172,20 @@ garf_bwd_kernel(const __grid_constant__ GarfBwdParams p) {
           const uint32_t acc_q = tmem_lane + (uint32_t)(st.src_col + 16 * cq);
           float acc3[3] = {0.f, 0.f, 0.f};
           uint32_t va[16], vb[16];
-          auto group = [&](const uint32_t (&v)[16], int j) {
+          // The residual-path gradient (d(z1 + z2[:, :128]), packed bf16, this thread's 2 x 16 columns) was parked in
+          // TMEM columns sigma_col .. + 63 by the NG_F_HOLD_SAVE step: sixteen registers held across ten steps cost
+          // the backward 9 % (spills, 2.65 -> 2.42 ms without them). TMEM lane = tile row, so every thread reads
+          // back exactly what it wrote; the compiler guarantees no op in between touches those columns.
+          auto group = [&](uint32_t (&v)[16], int j) {
             uint32_t dp[8];
+            if (add_hold && j < 2) {      // fetched where it is used and added to the accumulator values up front:
+              uint32_t hold[8];           // the element loop below carries no trace of it for the other steps
+              tmem_ld8(tmem_lane + (uint32_t)(st.sigma_col + 32 * j + 8 * cq), hold);
+              tmem_ld_wait8(hold);
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                v[i] = __float_as_uint(__uint_as_float(v[i]) + ((i & 1) ? bf_hi(hold[i >> 1]) : bf_lo(hold[i >> 1])));
+            }
             uint32_t zz[8];      // the z stash keeps a thread's 16 columns in natural order (garf_kernels.cuh)
 #pragma unroll
             for (int i = 0; i < 8; ++i) zz[i] = zq[j & 1].w[i];
@@ -192,8 +199,7 @@ garf_bwd_kernel(const __grid_constant__ GarfBwdParams p) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const int i = 4 * q + e;
-                float ga = __uint_as_float(v[i]);
-                if (add_hold && j < 2) ga += (e & 1) ? bf_hi(hold[j][i >> 1]) : bf_lo(hold[j][i >> 1]);
+                const float ga = __uint_as_float(v[i]);
                 const float z = (e & 1) ? bf_hi(zz[i >> 1]) : bf_lo(zz[i >> 1]);
                 const float t = z * cc[e];
                 dz[e] = ga * ex2f(z * t) * (t * kTwoLn2);                 // g * y * (-2 v z)
@@ -254,10 +260,8 @@ garf_bwd_kernel(const __grid_constant__ GarfBwdParams p) {
               tmem_ld_wait16(v);
 #pragma unroll
               for (int i = 0; i < 16; i += 2) dp[i >> 1] = pack_bf16(__uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-              if ((flags & NG_F_HOLD_SAVE) && j < 2) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) hold[j][i] = dp[i];
-              }
+              if ((flags & NG_F_HOLD_SAVE) && j < 2)      // parked in TMEM until the NG_F_HOLD_ADD step (see there)
+                tmem_st8(tmem_lane + (uint32_t)(st.sigma_col + 32 * j + 8 * cq), dp);
               const uint32_t sb = slab_base + (uint32_t)(st.out_slab + j) * NB_SLAB_BYTES;
               sts128g(sb + off0, dp[0], dp[1], dp[2], dp[3]);
               sts128g(sb + off1, dp[4], dp[5], dp[6], dp[7]);
@@ -268,6 +272,7 @@ garf_bwd_kernel(const __grid_constant__ GarfBwdParams p) {
             sts128g(sb + off0, cq == 0 ? pack_bf16(dsp, 0.f) : 0u, 0u, 0u, 0u);
             sts128g(sb + off1, 0u, 0u, 0u, 0u);
           }
+          if (flags & NG_F_HOLD_SAVE) tmem_st_wait();
           publish_step(sm, g, true, lane);
         } else {
           if (k < n_ops) publish_step(sm, g, false, lane);

@@ -136,6 +136,19 @@ class _Builder:
             raise RuntimeError(f"GARF program: {self.n_floats} packed floats exceed {_lib.NG_MAX_PROGRAM_FLOATS}")
         if self.steps[-1].wait_lag != 0:
             raise RuntimeError("GARF program: the last step must wait for the last op")
+        # the residual-path gradient parked in TMEM (backward: NG_F_HOLD_SAVE .. NG_F_HOLD_ADD, 64 columns at the steps'
+        # sigma_col): no op issued in between may write those columns
+        save = [k for k, st in enumerate(self.steps) if st.kind == NG_BSTEP_PLAIN and (st.flags & NG_F_HOLD_SAVE)]
+        add = [k for k, st in enumerate(self.steps) if st.kind == NG_BSTEP_ACT and (st.flags & NG_F_HOLD_ADD)]
+        if save or add:
+            if len(save) != 1 or len(add) != 1 or self.steps[save[0]].sigma_col != self.steps[add[0]].sigma_col:
+                raise RuntimeError("GARF program: the hold save / add steps do not pair up")
+            c0 = self.steps[save[0]].sigma_col
+            for k in range(save[0], add[0]):          # op k is issued after step k; the add step reads before op add[0]
+                for b in range(self.ops[k].n_blocks if self.ops[k].n_chunks else 0):
+                    blk = self.ops[k].blocks[b]
+                    if blk.tmem_col < c0 + 64 and c0 < blk.tmem_col + blk.n:
+                        raise RuntimeError(f"GARF program: op {k} overwrites the TMEM columns that hold the residual gradient")
         prog.n_ops = len(self.ops)
         prog.n_floats = self.n_floats
         for i, o in enumerate(self.ops):
@@ -327,7 +340,9 @@ def compile_radiance(L: List[GaussLinear], Lc: List[GaussLinear]) -> CompiledGar
     g.step(NG_BSTEP_ACT, n_slabs=4, out_slab=0, src_col=R0, coef_off=coef(C1, 0, 256), z_stash=zc1, y_stash=d_c1,
            skip_src=2, skip_off=g.pack_skip(C1.lin, 0, 256, 128))
     _mma_bwd(g, C1.lin, [0, 1, 2, 3], [(64 * c, 64) for c in range(4)], 0, 128, R1)
-    g.step(NG_BSTEP_PLAIN, n_slabs=2, out_slab=0, src_col=R1, flags=NG_F_HOLD_SAVE | NG_F_SIGMA, y_stash=d_8)
+    HOLD_COL = R0 + 128        # 64 TMEM columns no op touches between the save and the add (checked in finish())
+    g.step(NG_BSTEP_PLAIN, n_slabs=2, out_slab=0, src_col=R1, flags=NG_F_HOLD_SAVE | NG_F_SIGMA, y_stash=d_8,
+           sigma_col=HOLD_COL)
     _mma_bwd(g, L8.lin, [0, 1, 2], [(0, 64), (64, 64), (128, 1)], 0, 128, R0)
     g.step(NG_BSTEP_ACT, n_slabs=2, out_slab=0, src_col=R0, coef_off=coef(L7, 0, 128), z_stash=z7, y_stash=d_7)
     _mma_bwd(g, L7.lin, [0, 1], [(0, 64), (64, 64)], 0, 256, R1)
@@ -340,7 +355,7 @@ def compile_radiance(L: List[GaussLinear], Lc: List[GaussLinear]) -> CompiledGar
                z_stash=z5 + 2 * blk, y_stash=d_5 + 2 * blk, skip_src=1, skip_off=g.pack_skip(L5.lin, 128 * blk, 128, 128))
         _mma_bwd(g, L5.lin, [HOLD, HOLD + 1], [(128 * blk, 64), (128 * blk + 64, 64)], 0, 128, R1, accumulate=blk > 0)
     g.step(NG_BSTEP_ACT, n_slabs=2, out_slab=0, src_col=R1, coef_off=coef(L4, 0, 128), z_stash=z4, y_stash=d_4,
-           flags=NG_F_HOLD_ADD)                                           # + the residual path (z1 + z2)
+           flags=NG_F_HOLD_ADD, sigma_col=HOLD_COL)                       # + the residual path (z1 + z2)
     _mma_bwd(g, L4.lin, [0, 1], [(0, 64), (64, 64)], 0, 128, R0)
     g.step(NG_BSTEP_ACT, n_slabs=2, out_slab=0, src_col=R0, coef_off=coef(L3, 0, 128), z_stash=z3, y_stash=d_3)
     _mma_bwd(g, L3.lin, [0, 1], [(0, 64), (64, 64)], 0, 256, R1)
