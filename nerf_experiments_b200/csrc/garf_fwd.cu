@@ -113,6 +113,19 @@ garf_fwd_kernel(const __grid_constant__ GarfFwdParams p) {
         const uint32_t g = g0 + (uint32_t)k;
         const int through = (int)g - 1 - st.wait_lag;
         const int kind = st.kind, nsl = st.n_slabs;
+        // first-layer parameters of this lane's two columns: requested BEFORE the barrier waits (with 227 KB of
+        // shared memory carved out there is no L1 to speak of; each of these is an L2 round trip)
+        float gen_w[10];
+        if (kind == NG_STEP_GEN) {
+          const int col = st.gen_col0 + 64 * (warp & 1) + 2 * lane;
+          const float* W = p.params + prog.w1_off + (long long)col * 3;
+#pragma unroll
+          for (int i = 0; i < 6; ++i) gen_w[i] = __ldg(W + i);
+          gen_w[6] = __ldg(p.params + prog.b1_off + col);
+          gen_w[7] = __ldg(p.params + prog.b1_off + col + 1);
+          gen_w[8] = __ldg(p.params + prog.g1_off + col);
+          gen_w[9] = __ldg(p.params + prog.g1_off + col + 1);
+        }
         rs.acc_through(sm, through);
         if (training) rs.drain_through(sm, through);
         tcgen05_fence_after();
@@ -121,12 +134,8 @@ garf_fwd_kernel(const __grid_constant__ GarfFwdParams p) {
           // first layer, fp32: this warp covers 16 rows x one slab of the 128-column block, a lane
           // owns two adjacent columns (weights in registers, positions broadcast from shared memory)
           const int sib = warp & 1, rg = warp >> 1;
-          const int col = st.gen_col0 + 64 * sib + 2 * lane;
-          const float* W = p.params + prog.w1_off + (long long)col * 3;
-          const float w00 = __ldg(W + 0), w01 = __ldg(W + 1), w02 = __ldg(W + 2);
-          const float w10 = __ldg(W + 3), w11 = __ldg(W + 4), w12 = __ldg(W + 5);
-          const float b0 = __ldg(p.params + prog.b1_off + col), b1 = __ldg(p.params + prog.b1_off + col + 1);
-          const float s0 = __ldg(p.params + prog.g1_off + col), s1 = __ldg(p.params + prog.g1_off + col + 1);
+          const float w00 = gen_w[0], w01 = gen_w[1], w02 = gen_w[2], w10 = gen_w[3], w11 = gen_w[4], w12 = gen_w[5];
+          const float b0 = gen_w[6], b1 = gen_w[7], s0 = gen_w[8], s1 = gen_w[9];
           const float c0 = -(s0 * s0 + 1e-6f) * kLog2e, c1 = -(s1 * s1 + 1e-6f) * kLog2e;
           uint8_t* slab = sm.slab(st.out_slab + sib);
           uint32_t zp[16];
