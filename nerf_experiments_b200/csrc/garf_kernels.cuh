@@ -1,10 +1,10 @@
 // Shared pieces of the fused GARF field kernels (garf_fwd.cu, garf_bwd.cu): shared-memory
 // carve-up, the weight producer, the MMA issuer and the stash copier of an NgProgram
-// (include/nerfb200_garf.h). The hand-off protocol is deliberately simpler than the one of the ReLU
-// network (mlp_kernels.cuh): these kernels are bound by the HBM traffic of their stashes in
-// training, so an op starts when ALL of its inputs are published, not slab by slab.
+// (include/nerfb200_garf.h). The hand-off protocol is op-granular (an op starts when the step in front
+// of it is done) except behind the Gaussian steps, whose slabs are handed over one by one (slab_ready,
+// NgOp.early) so that the MMAs of op k run under the epilogue of step k.
 //
-// Barriers (all in shared memory, two of each, used alternately by the global op index g):
+// Barriers (all in shared memory; two of each op-granular kind, used alternately by the global op index g):
 //   in_ready[g & 1]  16 row warps -> MMA warp, stash warp: "step g is done": the inputs of op g are
 //                    in shared memory and no row thread reads the accumulator columns it overwrites
 //   acc_full[g & 1]  MMA warp (tcgen05.commit) -> row warps: op g and every op before it completed

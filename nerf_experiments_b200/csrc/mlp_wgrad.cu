@@ -14,7 +14,10 @@
 // GARF's Gaussian-width gradients (sum over samples of z * dz) ride the same way: an item with
 // "z duty" also streams the z slabs of some of its dY slabs into the stage (a stage holds up to
 // nine half slabs: dY | X | Z), so the dz slabs are read from HBM once for the weight block AND
-// the column sums; column-sum-only items (no weight block) take what does not fit.
+// the column sums; column-sum-only items (no weight block) take what does not fit. (The shipped GARF
+// programs no longer use the z duty: for y = exp(-z^2 v) the sum z dz follows from dW and db,
+// nerfb200_gauss_width_grad. It stays for activations whose parameter gradients do not reduce to those,
+// and is exercised through the C ABI by tests/test_gpu_wgrad_items.py.)
 #include "common.cuh"
 #include "mlp.h"
 #include "tc.cuh"
